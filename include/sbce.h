@@ -1,0 +1,159 @@
+/*
+ * sbce.h -- C ABI of the B200-native semi-blind EM channel estimator
+ * (MIMO-RIS link, pilots + unknown QAM data).
+ *
+ * The reference (a directory of Python scripts) has no FFI; its de-facto
+ * interface for this path is the family of estimator functions every driver
+ * calls:
+ *     em(Y_d,Y_p,T_d,T_p,Z_p,PsiTilde_td,all_possibleSymbols,M,varn,itera[,h_initial])
+ *         /root/reference/Proposed_method_NMSEvsTp.py:43
+ *         /root/reference/Proposed method/Proposed_method_NMSEvsTp.py:50
+ *     em (hard decisions, + LLF / + decisions)
+ *         /root/reference/Proposed method/ML_detecctor.py:51
+ *         /root/reference/Proposed method/SER/log_max_SER.py:51
+ *     em_ml /root/reference/Proposed method/PMvsMLvsZFvsMMSE.py:135
+ *     em_pm /root/reference/Proposed method/PM.py:47, PM_beta.py:42
+ * One batched entry point, sbce_em_batch(), replaces the body of all of them;
+ * the Python functions with the reference's names and argument order sit on
+ * top of it (package estimators.py) and INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every complex array is interleaved
+ *     (re,im) float64, i.e. numpy complex128 / torch.complex128 memory, C order.
+ *   - L = (N+1)*n_tx unknowns per receive antenna; the channel vector h of the
+ *     reference is viewed as Theta[L][n_rx] with Theta[n'*n_tx+j][r] =
+ *     h[(n'*n_tx+j)*n_rx+r]  (n'=0: direct link; Proposed method/PM.py:15).
+ *   - hypothesis index k = sum_j idx_j * M^(n_tx-1-j) (itertools.product order,
+ *     Proposed method/PM.py:25-31), constellation index = iQ*sqrt(M)+iI
+ *     (Proposed method/QAM.py:320-322).
+ *   - all calls are asynchronous on `stream` unless the name ends in _host;
+ *     the library keeps no global mutable state except a per-process scratch
+ *     cache used by the *_host convenience entry points.
+ *   - return value: 0 ok, <0 argument error (SBCE_E_*), >0 a cudaError_t.
+ *     Per-trial numerical status is reported in status[b] (bit mask).
+ */
+#ifndef SBCE_H
+#define SBCE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBCE_VERSION 100
+
+/* estimator modes */
+#define SBCE_MODE_SOFT 0    /* posterior-weighted statistics (em)                         */
+#define SBCE_MODE_HARD 1    /* arg-max hypothesis, rank-one statistics (em_ml / log-max)  */
+#define SBCE_MODE_PM 2      /* partitioned, candidate weight 1 (Proposed method/PM.py)    */
+#define SBCE_MODE_PM_BETA 3 /* partitioned, posterior over candidates (PM_beta.py)        */
+
+/* flags */
+#define SBCE_FLAG_GENIE_STOP 1u /* stop a trial when | ||theta|| - ||h_true|| | < 1 and l != 0 (PM.py:110)   */
+#define SBCE_FLAG_QUIRKS 2u     /* PM modes: reproduce the off-by-one psi slice (PM.py:63) and the un-permuted
+                                   candidate vector (PM.py:102); cleared = corrected behaviour             */
+#define SBCE_FLAG_PSI_SHARED 4u /* PsiP / PsiD are shared by all trials of the batch ([T][N+1], no batch dim) */
+#define SBCE_FLAG_ZERO_START 8u /* theta0 is ignored, EM starts from 0 (Proposed_method_NMSEvsTp.py:45)      */
+
+/* per-trial status bits */
+#define SBCE_ST_NOT_PD 1    /* non-positive pivot in the Cholesky of the normal matrix (singular M-step) */
+#define SBCE_ST_NONFINITE 2 /* a non-finite value appeared in theta                                      */
+
+/* argument errors */
+#define SBCE_E_NULL (-1)
+#define SBCE_E_SHAPE (-2)
+#define SBCE_E_UNSUPPORTED (-3)
+#define SBCE_E_WORKSPACE (-4)
+#define SBCE_E_NODEVICE (-5)
+
+typedef struct sbce_cfg {
+    int32_t N;            /* RIS elements; phase matrices have N+1 rows (row 0 = direct link) */
+    int32_t n_tx, n_rx;   /* transmit / receive antennas                                       */
+    int32_t M;            /* constellation order: 4, 16 or 64                                  */
+    int32_t T_p, T_d;     /* pilot / data block lengths                                        */
+    int32_t itera;        /* EM iterations                                                     */
+    int32_t batch;        /* trials B in this call                                             */
+    int32_t mode;         /* SBCE_MODE_*                                                       */
+    uint32_t flags;       /* SBCE_FLAG_*                                                       */
+    int32_t partition_p1; /* PM modes: p+1 = streams enumerated exhaustively (PM.py:74-75)     */
+    int32_t reserved[5];
+} sbce_cfg;
+
+/* Device (or, for *_host entry points, host) buffers of one batch.  Shapes in
+ * elements of complex128 unless stated; nullable ones are marked. */
+typedef struct sbce_io {
+    const double* Yd;      /* [B][T_d][n_rx]                                                   */
+    const double* Yp;      /* [B][T_p][n_rx]                                                   */
+    const double* PsiD;    /* [B][T_d][N+1]  (or [T_d][N+1] with SBCE_FLAG_PSI_SHARED)          */
+    const double* PsiP;    /* [B][T_p][N+1]  (or [T_p][N+1])                                   */
+    const double* Xp;      /* [B][T_p][n_tx] pilot symbols                                     */
+    const double* theta0;  /* [B][L][n_rx]   start point; nullable with SBCE_FLAG_ZERO_START   */
+    const double* varn;    /* [B] float64 -- the E-step divides by varn^2 (reference quirk Q1) */
+    const double* h_true;  /* [B][L][n_rx]   nullable: needed for nmse[] and the genie stop    */
+    const double* Xd_true; /* [B][T_d][n_tx] nullable: needed for llf[] (as-coded LLF)         */
+    double* theta;         /* [B][L][n_rx]   out                                               */
+    int32_t* kstar;        /* [B][T_d] int32 out, nullable: decisions of the last executed
+                              iteration, made before its M-step (SER/log_max_SER.py:77-78)     */
+    double* llf;           /* [B][itera] float64 out, nullable: LLF exactly as coded
+                              (ML_detecctor.py:84); entries of skipped iterations are NaN      */
+    double* lse;           /* [B][itera] float64 out, nullable: sum_t log sum_k exp(-d2/varn^2)
+                              at the theta that entered the iteration                          */
+    double* nmse;          /* [B] float64 out, nullable (needs h_true)                         */
+    int32_t* iters;        /* [B] int32 out, nullable: iterations executed                     */
+    int32_t* status;       /* [B] int32 out, nullable: SBCE_ST_* bit mask                      */
+} sbce_io;
+
+/* library / device probes */
+int sbce_version(void);
+const char* sbce_error_string(int code);
+int sbce_device_count(void);
+
+/* Bytes of device workspace needed to keep `trials_in_flight` trials of `cfg`
+ * in flight (cfg->batch is ignored).  sbce_em_batch() processes the batch in
+ * chunks of as many trials as the workspace it is given can hold. */
+int sbce_workspace_bytes(const sbce_cfg* cfg, int32_t trials_in_flight, size_t* bytes);
+
+/* The hot path: `itera` EM iterations for every trial of the batch.
+ * All pointers in `io` are DEVICE pointers; `stream` is a cudaStream_t. */
+int sbce_em_batch(const sbce_cfg* cfg, const sbce_io* io, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* Same, with HOST pointers in `io`: stages through pinned memory, copies
+ * host->device, runs sbce_em_batch on an internal stream, copies the outputs
+ * back and synchronises.  `device` selects the GPU. */
+int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device);
+
+/* Stand-alone E-step sweep (posterior statistics at a given theta), device
+ * pointers.  stat_m [B][T_d][n_tx], stat_R [B][T_d][n_tx][n_tx] complex128,
+ * kstar [B][T_d] int32 (nullable), lse_sym [B][T_d] float64 (nullable).
+ * Uses cfg->mode (SOFT/HARD/PM/PM_BETA) exactly as the EM loop does. */
+int sbce_estep(const sbce_cfg* cfg, const sbce_io* io, const double* theta, double* stat_m,
+               double* stat_R, int32_t* kstar, double* lse_sym, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+/* Stand-alone M-step (normal-equation build + Cholesky solve) from given data
+ * statistics; pilots enter with probability-one statistics.  theta_out [B][L][n_rx]. */
+int sbce_mstep(const sbce_cfg* cfg, const sbce_io* io, const double* stat_m, const double* stat_R,
+               double* theta_out, int32_t* status, void* workspace, size_t workspace_bytes,
+               void* stream);
+
+/* Per-sweep-point accumulation used before the cross-GPU sum:
+ * acc[0] += sum_b nmse[b] over trials with status==0, acc[1] += their count,
+ * acc[2] += count of trials with status!=0.  acc is 3 float64 on the device. */
+int sbce_accumulate_nmse(const double* nmse, const int32_t* status, int32_t batch, double* acc,
+                         void* stream);
+
+/* Measured FP64 FMA throughput of the current device (TFLOP/s, 2 flops per
+ * FMA), used as the roofline denominator for the FP64-bound kernels. */
+int sbce_measure_fp64_peak(double* tflops, double* seconds);
+
+/* Number of kernels this library launched since the last reset (for bench.py's
+ * gpu_launches claim). */
+int64_t sbce_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBCE_H */

@@ -1,0 +1,375 @@
+// C ABI of libsbce (declared in include/sbce.h): argument validation, workspace
+// carve-up, chunking of the batch, and the kernel schedule of the EM loop.
+#include <atomic>
+#include <mutex>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace sbce {
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int make_dims(const sbce_cfg* c, Dims* d) {
+    if (!c) return SBCE_E_NULL;
+    if (c->N < 1 || c->n_tx < 1 || c->n_rx < 1 || c->T_p < 0 || c->T_d < 1 || c->itera < 0 || c->batch < 0)
+        return SBCE_E_SHAPE;
+    int sq = 0;
+    if (c->M == 4) sq = 2; else if (c->M == 16) sq = 4; else if (c->M == 64) sq = 8; else return SBCE_E_UNSUPPORTED;
+    if (c->n_tx > 4) return SBCE_E_UNSUPPORTED;
+    if (!(c->n_rx <= 4 || c->n_rx == 6 || c->n_rx == 8)) return SBCE_E_UNSUPPORTED;
+    if (c->mode < SBCE_MODE_SOFT || c->mode > SBCE_MODE_PM_BETA) return SBCE_E_UNSUPPORTED;
+    d->N = c->N; d->N1 = c->N + 1; d->n_tx = c->n_tx; d->n_rx = c->n_rx; d->M = c->M; d->sqM = sq;
+    d->bitsM = (sq == 2 ? 2 : (sq == 4 ? 4 : 6));
+    d->T_p = c->T_p; d->T_d = c->T_d; d->itera = c->itera;
+    d->L = d->N1 * c->n_tx;
+    d->Lp = (d->L + 3) & ~3;
+    d->RP = (c->n_rx + 3) & ~3;
+    d->Ltot = d->Lp + d->RP;
+    d->mode = c->mode; d->flags = c->flags; d->p1 = c->partition_p1;
+    d->psi_shared = (c->flags & SBCE_FLAG_PSI_SHARED) ? 1 : 0;
+    d->rec = qr_record_doubles(c->n_tx);
+    if (c->mode >= SBCE_MODE_PM) {
+        if (c->partition_p1 < 1 || c->partition_p1 > c->n_tx) return SBCE_E_SHAPE;
+        if (c->n_rx < c->n_tx) return SBCE_E_UNSUPPORTED;
+    }
+    return 0;
+}
+
+static inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t carve_workspace(const Dims& d, int nb, void* base, Workspace* ws) {
+    size_t off = 0;
+    char* p = (char*)base;
+    auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += al(bytes); return r; };
+    const size_t B = (size_t)nb;
+    ws->stat_m = (double*)take(B * d.T_d * d.n_tx * 16);
+    ws->stat_R = (double*)take(B * d.T_d * d.n_tx * d.n_tx * 16);
+    ws->pil_m = (double*)take(B * d.T_p * d.n_tx * 16 + 16);
+    ws->pil_R = (double*)take(B * d.T_p * d.n_tx * d.n_tx * 16 + 16);
+    ws->qr = (double*)take(B * d.T_d * d.rec * 8);
+    ws->lse_sym = (double*)take(B * d.T_d * 8);
+    ws->Gp = (double*)take(B * d.Ltot * d.Lp * 16);
+    ws->G = (double*)take(B * d.Ltot * d.Lp * 16);
+    ws->active = (int32_t*)take(B * 4);
+    ws->stat = (int32_t*)take(B * 4);
+    ws->kscratch = (int32_t*)take(B * d.T_d * 4);
+    ws->bytes = off;
+    return off;
+}
+
+#define CK(x)                                  \
+    do {                                       \
+        cudaError_t _e = (x);                  \
+        if (_e != cudaSuccess) return (int)_e; \
+    } while (0)
+
+// forward declaration (pm.cu)
+cudaError_t launch_pm_stats(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
+                            const double* varn, const int32_t* active, double* stat_m, double* stat_R,
+                            cudaStream_t s);
+
+static int estep_dispatch(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
+                          const double* varn, const int32_t* active, Workspace& ws, double* stat_m, double* stat_R,
+                          int32_t* kstar, double* lse_sym, cudaStream_t s) {
+    if (d.mode == SBCE_MODE_SOFT || d.mode == SBCE_MODE_HARD) {
+        CK(launch_estep(d, nb, Yd, PsiD, theta, varn, active, ws.qr, stat_m, stat_R, kstar, lse_sym, s));
+    } else {
+        CK(launch_pm_stats(d, nb, Yd, PsiD, theta, varn, active, stat_m, stat_R, s));
+    }
+    return 0;
+}
+
+static int em_chunk(const Dims& d, int nb, const sbce_io& io, Workspace& ws, cudaStream_t s) {
+    CK(launch_init_state(d, nb, io.theta0, io.theta, ws.active, ws.stat, io.iters, io.llf, io.lse, s));
+    // pilot part of the normal equations, once (the reference recomputes it every iteration:
+    // Proposed_method_NMSEvsTp.py:63-65)
+    CK(launch_pilot_stats(d, nb, io.Xp, ws.pil_m, ws.pil_R, s));
+    CK(launch_gram(d, nb, io.PsiP, d.T_p, io.Yp, ws.pil_m, ws.pil_R, nullptr, ws.Gp, nullptr, s));
+    for (int l = 0; l < d.itera; ++l) {
+        int rc = estep_dispatch(d, nb, io.Yd, io.PsiD, io.theta, io.varn, ws.active, ws, ws.stat_m, ws.stat_R,
+                                io.kstar, ws.lse_sym, s);
+        if (rc) return rc;
+        CK(launch_gram(d, nb, io.PsiD, d.T_d, io.Yd, ws.stat_m, ws.stat_R, ws.Gp, ws.G, ws.active, s));
+        CK(launch_chol_solve(d, nb, ws.G, io.theta, ws.active, ws.stat, s));
+        CK(launch_after_iteration(d, nb, l, io.theta, io.h_true, io.Yp, io.Yd, io.PsiP, io.PsiD, io.Xp, io.Xd_true,
+                                  io.varn, ws.lse_sym, ws.active, io.iters, io.llf, io.lse, s));
+    }
+    CK(launch_final_metrics(d, nb, io.theta, io.h_true, ws.stat, io.nmse, io.status, s));
+    return 0;
+}
+
+static sbce_io offset_io(const Dims& d, const sbce_io& io, size_t b0) {
+    sbce_io o = io;
+    const size_t Ln = (size_t)d.L * d.n_rx * 2;
+    auto adv = [](const double* p, size_t n) { return p ? p + n : p; };
+    auto advw = [](double* p, size_t n) { return p ? p + n : p; };
+    o.Yd = adv(io.Yd, b0 * d.T_d * d.n_rx * 2);
+    o.Yp = adv(io.Yp, b0 * d.T_p * d.n_rx * 2);
+    if (!d.psi_shared) {
+        o.PsiD = adv(io.PsiD, b0 * d.T_d * d.N1 * 2);
+        o.PsiP = adv(io.PsiP, b0 * d.T_p * d.N1 * 2);
+    }
+    o.Xp = adv(io.Xp, b0 * d.T_p * d.n_tx * 2);
+    o.theta0 = adv(io.theta0, b0 * Ln);
+    o.varn = adv(io.varn, b0);
+    o.h_true = adv(io.h_true, b0 * Ln);
+    o.Xd_true = adv(io.Xd_true, b0 * d.T_d * d.n_tx * 2);
+    o.theta = advw(io.theta, b0 * Ln);
+    o.kstar = io.kstar ? io.kstar + b0 * d.T_d : nullptr;
+    o.llf = advw(io.llf, b0 * d.itera);
+    o.lse = advw(io.lse, b0 * d.itera);
+    o.nmse = advw(io.nmse, b0);
+    o.iters = io.iters ? io.iters + b0 : nullptr;
+    o.status = io.status ? io.status + b0 : nullptr;
+    return o;
+}
+
+static int check_io(const Dims& d, const sbce_io* io) {
+    if (!io) return SBCE_E_NULL;
+    if (!io->Yd || !io->PsiD || !io->varn || !io->theta) return SBCE_E_NULL;
+    if (d.T_p > 0 && (!io->Yp || !io->PsiP || !io->Xp)) return SBCE_E_NULL;
+    if (!(d.flags & SBCE_FLAG_ZERO_START) && !io->theta0) return SBCE_E_NULL;
+    if ((d.flags & SBCE_FLAG_GENIE_STOP) && !io->h_true) return SBCE_E_NULL;
+    return 0;
+}
+
+}  // namespace sbce
+
+using namespace sbce;
+
+extern "C" {
+
+int sbce_version(void) { return SBCE_VERSION; }
+
+const char* sbce_error_string(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case SBCE_E_NULL: return "required pointer is null";
+        case SBCE_E_SHAPE: return "invalid shape parameter";
+        case SBCE_E_UNSUPPORTED: return "unsupported configuration (n_tx<=4, n_rx in {1,2,3,4,6,8}, M in {4,16,64})";
+        case SBCE_E_WORKSPACE: return "workspace too small for one trial";
+        case SBCE_E_NODEVICE: return "no CUDA device";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int sbce_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int sbce_workspace_bytes(const sbce_cfg* cfg, int32_t trials_in_flight, size_t* bytes) {
+    Dims d;
+    int rc = make_dims(cfg, &d);
+    if (rc) return rc;
+    if (!bytes) return SBCE_E_NULL;
+    if (trials_in_flight < 1) return SBCE_E_SHAPE;
+    Workspace ws;
+    *bytes = carve_workspace(d, trials_in_flight, nullptr, &ws);
+    return 0;
+}
+
+static int trials_fitting(const Dims& d, size_t bytes, int want) {
+    Workspace ws;
+    if (carve_workspace(d, 1, nullptr, &ws) > bytes) return 0;
+    int lo = 1, hi = want;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) / 2;
+        if (carve_workspace(d, mid, nullptr, &ws) <= bytes) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+int sbce_em_batch(const sbce_cfg* cfg, const sbce_io* io, void* workspace, size_t workspace_bytes, void* stream) {
+    Dims d;
+    int rc = make_dims(cfg, &d);
+    if (rc) return rc;
+    rc = check_io(d, io);
+    if (rc) return rc;
+    if (cfg->batch == 0) return 0;
+    if (!workspace) return SBCE_E_NULL;
+    const int chunk = trials_fitting(d, workspace_bytes, cfg->batch);
+    if (chunk < 1) return SBCE_E_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int b0 = 0; b0 < cfg->batch; b0 += chunk) {
+        const int nb = (cfg->batch - b0 < chunk) ? cfg->batch - b0 : chunk;
+        Workspace ws;
+        carve_workspace(d, nb, workspace, &ws);
+        sbce_io o = offset_io(d, *io, (size_t)b0);
+        rc = em_chunk(d, nb, o, ws, s);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int sbce_estep(const sbce_cfg* cfg, const sbce_io* io, const double* theta, double* stat_m, double* stat_R,
+               int32_t* kstar, double* lse_sym, void* workspace, size_t workspace_bytes, void* stream) {
+    Dims d;
+    int rc = make_dims(cfg, &d);
+    if (rc) return rc;
+    if (!io || !io->Yd || !io->PsiD || !io->varn || !theta || !stat_m || !stat_R || !workspace) return SBCE_E_NULL;
+    if (cfg->batch == 0) return 0;
+    const int chunk = trials_fitting(d, workspace_bytes, cfg->batch);
+    if (chunk < 1) return SBCE_E_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int b0 = 0; b0 < cfg->batch; b0 += chunk) {
+        const int nb = (cfg->batch - b0 < chunk) ? cfg->batch - b0 : chunk;
+        Workspace ws;
+        carve_workspace(d, nb, workspace, &ws);
+        sbce_io o = offset_io(d, *io, (size_t)b0);
+        const size_t sb = (size_t)b0 * d.T_d;
+        rc = estep_dispatch(d, nb, o.Yd, o.PsiD, theta + (size_t)b0 * d.L * d.n_rx * 2, o.varn, nullptr, ws,
+                            stat_m + sb * d.n_tx * 2, stat_R + sb * d.n_tx * d.n_tx * 2, kstar ? kstar + sb : nullptr,
+                            lse_sym ? lse_sym + sb : nullptr, s);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int sbce_mstep(const sbce_cfg* cfg, const sbce_io* io, const double* stat_m, const double* stat_R, double* theta_out,
+               int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+    Dims d;
+    int rc = make_dims(cfg, &d);
+    if (rc) return rc;
+    if (!io || !io->Yd || !io->PsiD || !stat_m || !stat_R || !theta_out || !workspace) return SBCE_E_NULL;
+    if (d.T_p > 0 && (!io->Yp || !io->PsiP || !io->Xp)) return SBCE_E_NULL;
+    if (cfg->batch == 0) return 0;
+    const int chunk = trials_fitting(d, workspace_bytes, cfg->batch);
+    if (chunk < 1) return SBCE_E_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int b0 = 0; b0 < cfg->batch; b0 += chunk) {
+        const int nb = (cfg->batch - b0 < chunk) ? cfg->batch - b0 : chunk;
+        Workspace ws;
+        carve_workspace(d, nb, workspace, &ws);
+        sbce_io o = offset_io(d, *io, (size_t)b0);
+        const size_t sb = (size_t)b0 * d.T_d;
+        CK(cudaMemsetAsync(ws.stat, 0, (size_t)nb * 4, s));
+        CK(launch_pilot_stats(d, nb, o.Xp, ws.pil_m, ws.pil_R, s));
+        CK(launch_gram(d, nb, o.PsiP, d.T_p, o.Yp, ws.pil_m, ws.pil_R, nullptr, ws.Gp, nullptr, s));
+        CK(launch_gram(d, nb, o.PsiD, d.T_d, o.Yd, stat_m + sb * d.n_tx * 2, stat_R + sb * d.n_tx * d.n_tx * 2, ws.Gp,
+                       ws.G, nullptr, s));
+        CK(launch_chol_solve(d, nb, ws.G, theta_out + (size_t)b0 * d.L * d.n_rx * 2, nullptr, ws.stat, s));
+        if (status) CK(cudaMemcpyAsync(status + b0, ws.stat, (size_t)nb * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+int sbce_accumulate_nmse(const double* nmse, const int32_t* status, int32_t batch, double* acc, void* stream) {
+    if (!nmse || !acc) return SBCE_E_NULL;
+    CK(launch_accumulate_nmse(nmse, status, batch, acc, (cudaStream_t)stream));
+    return 0;
+}
+
+int sbce_measure_fp64_peak(double* tflops, double* seconds) {
+    CK(run_fp64_peak(tflops, seconds));
+    return 0;
+}
+
+int64_t sbce_launch_count(int32_t reset) {
+    long long v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return (int64_t)v;
+}
+
+// ---------------------------------------------------------------------------
+// host-pointer convenience path (the end-to-end route the Python estimators use)
+// ---------------------------------------------------------------------------
+namespace {
+struct DevPool {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaStream_t stream = nullptr;
+};
+std::mutex g_mu;
+DevPool g_pool[16];
+
+int pool_get(int dev, size_t bytes, DevPool** out) {
+    DevPool& P = g_pool[dev];
+    if (!P.stream) CK(cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking));
+    if (P.cap < bytes) {
+        if (P.p) CK(cudaFree(P.p));
+        P.p = nullptr;
+        P.cap = 0;
+        CK(cudaMalloc(&P.p, bytes));
+        P.cap = bytes;
+    }
+    *out = &P;
+    return 0;
+}
+}  // namespace
+
+int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device) {
+    Dims d;
+    int rc = make_dims(cfg, &d);
+    if (rc) return rc;
+    rc = check_io(d, io);
+    if (rc) return rc;
+    if (cfg->batch == 0) return 0;
+    if (device < 0 || device >= 16 || device >= sbce_device_count()) return SBCE_E_NODEVICE;
+    std::lock_guard<std::mutex> lock(g_mu);
+    CK(cudaSetDevice(device));
+    const size_t B = (size_t)cfg->batch;
+    const size_t Ln = (size_t)d.L * d.n_rx * 16;
+    const size_t psiB = d.psi_shared ? 1 : B;
+    // device mirror of the io block
+    struct Seg { const void* h; size_t bytes; size_t off; bool in; void* hout; };
+    size_t off = 0;
+    auto seg = [&](const void* h, size_t bytes, bool in, void* hout) {
+        Seg s{h, bytes, off, in, hout};
+        if (h || hout) off += al(bytes);
+        return s;
+    };
+    Seg sYd = seg(io->Yd, B * d.T_d * d.n_rx * 16, true, nullptr);
+    Seg sYp = seg(io->Yp, B * d.T_p * d.n_rx * 16, true, nullptr);
+    Seg sPd = seg(io->PsiD, psiB * d.T_d * d.N1 * 16, true, nullptr);
+    Seg sPp = seg(io->PsiP, psiB * d.T_p * d.N1 * 16, true, nullptr);
+    Seg sXp = seg(io->Xp, B * d.T_p * d.n_tx * 16, true, nullptr);
+    Seg sT0 = seg(io->theta0, B * Ln, true, nullptr);
+    Seg sVn = seg(io->varn, B * 8, true, nullptr);
+    Seg sHt = seg(io->h_true, B * Ln, true, nullptr);
+    Seg sXd = seg(io->Xd_true, B * d.T_d * d.n_tx * 16, true, nullptr);
+    Seg oTh = seg(nullptr, B * Ln, false, io->theta);
+    Seg oKs = seg(nullptr, B * d.T_d * 4, false, io->kstar);
+    Seg oLl = seg(nullptr, B * d.itera * 8, false, io->llf);
+    Seg oLs = seg(nullptr, B * d.itera * 8, false, io->lse);
+    Seg oNm = seg(nullptr, B * 8, false, io->nmse);
+    Seg oIt = seg(nullptr, B * 4, false, io->iters);
+    Seg oSt = seg(nullptr, B * 4, false, io->status);
+    const size_t io_bytes = off;
+    // workspace: as many trials in flight as fit in ~1/3 of free memory, at most the batch
+    size_t freeb = 0, totalb = 0;
+    CK(cudaMemGetInfo(&freeb, &totalb));
+    size_t per1 = 0, perB = 0;
+    { Workspace w; per1 = carve_workspace(d, 1, nullptr, &w); perB = carve_workspace(d, cfg->batch, nullptr, &w); }
+    size_t budget = (freeb + g_pool[device].cap) / 3;
+    if (budget < per1) budget = per1;
+    size_t ws_bytes = perB < budget ? perB : budget;
+    DevPool* P = nullptr;
+    rc = pool_get(device, io_bytes + ws_bytes + 256, &P);
+    if (rc) return rc;
+    char* base = (char*)P->p;
+    cudaStream_t s = P->stream;
+    Seg* ins[] = {&sYd, &sYp, &sPd, &sPp, &sXp, &sT0, &sVn, &sHt, &sXd};
+    for (Seg* q : ins)
+        if (q->h && q->bytes) CK(cudaMemcpyAsync(base + q->off, q->h, q->bytes, cudaMemcpyHostToDevice, s));
+    sbce_io dio;
+    memset(&dio, 0, sizeof(dio));
+    auto dp = [&](const Seg& q) { return (q.h || q.hout) ? (double*)(base + q.off) : nullptr; };
+    dio.Yd = dp(sYd); dio.Yp = dp(sYp); dio.PsiD = dp(sPd); dio.PsiP = dp(sPp); dio.Xp = dp(sXp);
+    dio.theta0 = dp(sT0); dio.varn = dp(sVn); dio.h_true = dp(sHt); dio.Xd_true = dp(sXd);
+    dio.theta = dp(oTh); dio.kstar = (int32_t*)dp(oKs); dio.llf = dp(oLl); dio.lse = dp(oLs); dio.nmse = dp(oNm);
+    dio.iters = (int32_t*)dp(oIt); dio.status = (int32_t*)dp(oSt);
+    rc = sbce_em_batch(cfg, &dio, base + al(io_bytes), ws_bytes, (void*)s);
+    if (rc) return rc;
+    Seg* outs[] = {&oTh, &oKs, &oLl, &oLs, &oNm, &oIt, &oSt};
+    for (Seg* q : outs)
+        if (q->hout && q->bytes) CK(cudaMemcpyAsync(q->hout, base + q->off, q->bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // extern "C"

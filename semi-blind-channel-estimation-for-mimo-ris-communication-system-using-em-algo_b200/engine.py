@@ -1,0 +1,266 @@
+"""Batched host-side interface to libsbce: one call = `itera` EM iterations for a
+batch of Monte-Carlo trials laid out as structure-of-arrays (one contiguous
+complex128 array per quantity, trial index outermost).
+
+Two routes, both through the C ABI (include/sbce.h):
+  * run_host(...)   numpy in / numpy out  -> sbce_em_batch_host (H2D, kernels, D2H)
+  * run_device(...) torch.cuda tensors    -> sbce_em_batch on the current stream
+PyTorch is only the device allocator / stream provider here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import (FLAG_GENIE_STOP, FLAG_PSI_SHARED, FLAG_QUIRKS, FLAG_ZERO_START, MODE_HARD, MODE_PM,
+                   MODE_PM_BETA, MODE_SOFT)
+
+MODES = {"soft": MODE_SOFT, "hard": MODE_HARD, "pm": MODE_PM, "pm_beta": MODE_PM_BETA}
+
+
+@dataclass
+class Problem:
+    """Static shape/mode description of a batch (the former module globals of the
+    reference scripts: N, n_tx, n_rx, M_symbols, T_p, T_d, itera ...)."""
+    N: int
+    n_tx: int
+    n_rx: int
+    M: int
+    T_p: int
+    T_d: int
+    itera: int
+    mode: str = "soft"
+    genie_stop: bool = False
+    quirks: bool = True
+    zero_start: bool = False
+    psi_shared: bool = False
+    partition_r: float = 0.0
+
+    @property
+    def L(self):
+        return (self.N + 1) * self.n_tx
+
+    @property
+    def p1(self):
+        # Proposed method/PM.py:74-75: p = int(partition_r / log2 M), A holds p+1 streams
+        return int(self.partition_r / math.log2(self.M)) + 1
+
+    def cfg(self, batch):
+        flags = 0
+        flags |= FLAG_GENIE_STOP if self.genie_stop else 0
+        flags |= FLAG_QUIRKS if self.quirks else 0
+        flags |= FLAG_PSI_SHARED if self.psi_shared else 0
+        flags |= FLAG_ZERO_START if self.zero_start else 0
+        c = _lib.Cfg()
+        c.N, c.n_tx, c.n_rx, c.M = self.N, self.n_tx, self.n_rx, self.M
+        c.T_p, c.T_d, c.itera, c.batch = self.T_p, self.T_d, self.itera, batch
+        c.mode, c.flags, c.partition_p1 = MODES[self.mode], flags, self.p1
+        return c
+
+    def shapes(self, B):
+        pb = () if self.psi_shared else (B,)
+        return dict(Yd=(B, self.T_d, self.n_rx), Yp=(B, self.T_p, self.n_rx), PsiD=pb + (self.T_d, self.N + 1),
+                    PsiP=pb + (self.T_p, self.N + 1), Xp=(B, self.T_p, self.n_tx), theta0=(B, self.L, self.n_rx),
+                    h_true=(B, self.L, self.n_rx), Xd_true=(B, self.T_d, self.n_tx))
+
+
+@dataclass
+class Result:
+    theta: object
+    kstar: object = None
+    llf: object = None
+    lse: object = None
+    nmse: object = None
+    iters: object = None
+    status: object = None
+
+
+_IN_C = ("Yd", "Yp", "PsiD", "PsiP", "Xp", "theta0", "h_true", "Xd_true")
+
+
+def _np_c128(a, shape, name):
+    a = np.ascontiguousarray(a, dtype=np.complex128)
+    if a.shape != tuple(shape):
+        raise ValueError("%s has shape %s, expected %s" % (name, a.shape, tuple(shape)))
+    return a
+
+
+def run_host(prob: Problem, Yd, Yp, PsiD, PsiP, Xp, varn, theta0=None, h_true=None, Xd_true=None,
+             want=("kstar", "llf", "lse", "nmse", "iters", "status"), device=0) -> Result:
+    """numpy route (host buffers; copies are inside the call)."""
+    lib = _lib.require_device()
+    B = int(np.asarray(Yd).shape[0])
+    sh = prob.shapes(B)
+    ins = dict(Yd=Yd, Yp=Yp, PsiD=PsiD, PsiP=PsiP, Xp=Xp, theta0=theta0, h_true=h_true, Xd_true=Xd_true)
+    keep = {}
+    io = _lib.Io()
+    for k in _IN_C:
+        v = ins[k]
+        if v is None:
+            setattr(io, k, None)
+            continue
+        a = _np_c128(v, sh[k], k)
+        keep[k] = a
+        setattr(io, k, a.ctypes.data)
+    vn = np.ascontiguousarray(np.broadcast_to(np.asarray(varn, dtype=np.float64), (B,)))
+    keep["varn"] = vn
+    io.varn = vn.ctypes.data
+    out = Result(theta=np.empty((B, prob.L, prob.n_rx), dtype=np.complex128))
+    io.theta = out.theta.ctypes.data
+    if "kstar" in want:
+        out.kstar = np.empty((B, prob.T_d), dtype=np.int32)
+        io.kstar = out.kstar.ctypes.data
+    if "llf" in want and Xd_true is not None:
+        out.llf = np.empty((B, prob.itera), dtype=np.float64)
+        io.llf = out.llf.ctypes.data
+    if "lse" in want:
+        out.lse = np.empty((B, prob.itera), dtype=np.float64)
+        io.lse = out.lse.ctypes.data
+    if "nmse" in want and h_true is not None:
+        out.nmse = np.empty((B,), dtype=np.float64)
+        io.nmse = out.nmse.ctypes.data
+    if "iters" in want:
+        out.iters = np.empty((B,), dtype=np.int32)
+        io.iters = out.iters.ctypes.data
+    if "status" in want:
+        out.status = np.empty((B,), dtype=np.int32)
+        io.status = out.status.ctypes.data
+    cfg = prob.cfg(B)
+    _lib.check(lib.sbce_em_batch_host(C.byref(cfg), C.byref(io), device))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# device route (torch tensors as device memory)
+# ---------------------------------------------------------------------------
+
+def _t_ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def workspace_bytes(prob: Problem, trials_in_flight: int) -> int:
+    lib = _lib.load()
+    n = C.c_size_t(0)
+    cfg = prob.cfg(trials_in_flight)
+    _lib.check(lib.sbce_workspace_bytes(C.byref(cfg), trials_in_flight, C.byref(n)))
+    return int(n.value)
+
+
+class DeviceSession:
+    """Holds the device workspace for a Problem and launches on torch's current stream."""
+
+    def __init__(self, prob: Problem, trials_in_flight: int, device=None):
+        import torch
+
+        self.torch = torch
+        self.lib = _lib.require_device()
+        self.prob = prob
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.trials_in_flight = int(trials_in_flight)
+        self.ws_bytes = workspace_bytes(prob, self.trials_in_flight)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+
+    def _check(self, t, shape, name, dtype):
+        torch = self.torch
+        if t is None:
+            return None
+        if t.dtype != dtype or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+            raise ValueError("%s must be a contiguous cuda %s tensor of shape %s (got %s %s)" %
+                             (name, dtype, tuple(shape), t.dtype, tuple(t.shape)))
+        return t
+
+    def alloc_outputs(self, B, llf=False, lse=True, nmse=True, kstar=True):
+        torch, p = self.torch, self.prob
+        dev = self.device
+        return Result(theta=torch.empty((B, p.L, p.n_rx), dtype=torch.complex128, device=dev),
+                      kstar=torch.empty((B, p.T_d), dtype=torch.int32, device=dev) if kstar else None,
+                      llf=torch.empty((B, p.itera), dtype=torch.float64, device=dev) if llf else None,
+                      lse=torch.empty((B, p.itera), dtype=torch.float64, device=dev) if lse else None,
+                      nmse=torch.empty((B,), dtype=torch.float64, device=dev) if nmse else None,
+                      iters=torch.empty((B,), dtype=torch.int32, device=dev),
+                      status=torch.empty((B,), dtype=torch.int32, device=dev))
+
+    def _io(self, B, Yd, Yp, PsiD, PsiP, Xp, varn, theta0, h_true, Xd_true):
+        torch, p = self.torch, self.prob
+        sh = p.shapes(B)
+        c128 = torch.complex128
+        io = _lib.Io()
+        io.Yd = _t_ptr(self._check(Yd, sh["Yd"], "Yd", c128))
+        io.Yp = _t_ptr(self._check(Yp, sh["Yp"], "Yp", c128))
+        io.PsiD = _t_ptr(self._check(PsiD, sh["PsiD"], "PsiD", c128))
+        io.PsiP = _t_ptr(self._check(PsiP, sh["PsiP"], "PsiP", c128))
+        io.Xp = _t_ptr(self._check(Xp, sh["Xp"], "Xp", c128))
+        io.theta0 = _t_ptr(self._check(theta0, sh["theta0"], "theta0", c128))
+        io.h_true = _t_ptr(self._check(h_true, sh["h_true"], "h_true", c128))
+        io.Xd_true = _t_ptr(self._check(Xd_true, sh["Xd_true"], "Xd_true", c128))
+        io.varn = _t_ptr(self._check(varn, (B,), "varn", torch.float64))
+        return io
+
+    def run(self, Yd, Yp, PsiD, PsiP, Xp, varn, theta0=None, h_true=None, Xd_true=None, out: Optional[Result] = None):
+        """Asynchronous on torch's current stream; returns the (device) Result."""
+        torch, p = self.torch, self.prob
+        B = int(Yd.shape[0])
+        io = self._io(B, Yd, Yp, PsiD, PsiP, Xp, varn, theta0, h_true, Xd_true)
+        if out is None:
+            out = self.alloc_outputs(B, llf=Xd_true is not None, nmse=h_true is not None)
+        io.theta = _t_ptr(out.theta)
+        io.kstar = _t_ptr(out.kstar)
+        io.llf = _t_ptr(out.llf) if Xd_true is not None else None
+        io.lse = _t_ptr(out.lse)
+        io.nmse = _t_ptr(out.nmse) if h_true is not None else None
+        io.iters = _t_ptr(out.iters)
+        io.status = _t_ptr(out.status)
+        cfg = p.cfg(B)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.sbce_em_batch(C.byref(cfg), C.byref(io), self.ws.data_ptr(), self.ws_bytes, stream))
+        return out
+
+    def estep(self, Yd, PsiD, theta, varn):
+        """Stand-alone E-step sweep at `theta` -> (m, R, kstar, lse_sym) device tensors."""
+        torch, p = self.torch, self.prob
+        B = int(Yd.shape[0])
+        io = self._io(B, Yd, None, PsiD, None, None, varn, None, None, None)
+        dev = self.device
+        m = torch.empty((B, p.T_d, p.n_tx), dtype=torch.complex128, device=dev)
+        R = torch.empty((B, p.T_d, p.n_tx, p.n_tx), dtype=torch.complex128, device=dev)
+        ks = torch.empty((B, p.T_d), dtype=torch.int32, device=dev)
+        ls = torch.empty((B, p.T_d), dtype=torch.float64, device=dev)
+        self._check(theta, (B, p.L, p.n_rx), "theta", torch.complex128)
+        cfg = p.cfg(B)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self.lib.sbce_estep(C.byref(cfg), C.byref(io), theta.data_ptr(), m.data_ptr(), R.data_ptr(),
+                                       ks.data_ptr(), ls.data_ptr(), self.ws.data_ptr(), self.ws_bytes, stream))
+        return m, R, ks, ls
+
+    def mstep(self, Yd, Yp, PsiD, PsiP, Xp, stat_m, stat_R):
+        """Stand-alone M-step from given data statistics -> (theta, status)."""
+        torch, p = self.torch, self.prob
+        B = int(Yd.shape[0])
+        dev = self.device
+        varn = torch.ones((B,), dtype=torch.float64, device=dev)
+        io = self._io(B, Yd, Yp, PsiD, PsiP, Xp, varn, None, None, None)
+        self._check(stat_m, (B, p.T_d, p.n_tx), "stat_m", torch.complex128)
+        self._check(stat_R, (B, p.T_d, p.n_tx, p.n_tx), "stat_R", torch.complex128)
+        theta = torch.empty((B, p.L, p.n_rx), dtype=torch.complex128, device=dev)
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+        cfg = p.cfg(B)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self.lib.sbce_mstep(C.byref(cfg), C.byref(io), stat_m.data_ptr(), stat_R.data_ptr(),
+                                       theta.data_ptr(), status.data_ptr(), self.ws.data_ptr(), self.ws_bytes, stream))
+        return theta, status
+
+
+def fp64_peak_tflops():
+    lib = _lib.require_device()
+    tf, sec = C.c_double(0), C.c_double(0)
+    _lib.check(lib.sbce_measure_fp64_peak(C.byref(tf), C.byref(sec)))
+    return float(tf.value)
+
+
+def launch_count(reset=False):
+    return int(_lib.load().sbce_launch_count(1 if reset else 0))

@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the numpy oracle on
+identical seeded inputs, and against the golden vectors minted from the literal
+reference.  Bars (BASELINE.json north_star): theta within 1e-9 relative Frobenius at
+equal iteration count, hard-decision indices bit-exact, NMSE to 4 significant figures."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def relerr(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))
+
+
+@pytest.fixture(scope="module")
+def S(cuda_device):
+    import sbce
+
+    sbce._lib.require_device()
+    return sbce
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import em_numpy
+
+    return em_numpy
+
+
+ESTEP_CASES = [
+    # N, n_tx, n_rx, M, T_d, varn
+    (8, 1, 1, 4, 20, 0.5), (8, 1, 4, 16, 20, 0.3), (12, 1, 8, 64, 12, 0.4),
+    (8, 2, 2, 4, 33, 0.1), (8, 2, 2, 4, 33, 3.0), (8, 2, 4, 16, 17, 0.3), (6, 2, 3, 64, 9, 0.5),
+    (7, 3, 3, 4, 21, 0.2), (5, 3, 4, 16, 10, 1.5), (5, 3, 2, 4, 10, 0.7),
+    (9, 4, 4, 4, 19, 0.1), (6, 4, 4, 16, 6, 0.5), (6, 4, 4, 16, 6, 30.0), (4, 4, 6, 4, 7, 0.4), (4, 2, 8, 4, 7, 0.4),
+]
+
+
+@pytest.mark.parametrize("case", ESTEP_CASES)
+@pytest.mark.parametrize("hard", [False, True])
+def test_estep_matches_oracle(S, orc, case, hard):
+    import torch
+
+    N, n_tx, n_rx, M, T_d, varn = case
+    B = 3
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, 4, T_d, varn, B, seed=100 + N, legacy=False)
+    rng = np.random.default_rng(7)
+    # theta near the truth (peaked posteriors) for b=0,1 and far (flat-ish) for b=2
+    theta = tb.h + 0.05 * (rng.standard_normal(tb.h.shape) + 1j * rng.standard_normal(tb.h.shape))
+    theta[2] = 0.3 * tb.h[2]
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=4, T_d=T_d, itera=1, mode="hard" if hard else "soft")
+    ses = S.DeviceSession(prob, B)
+    dev = ses.device
+    m, R, ks, ls = ses.estep(torch.from_numpy(tb.Yd).to(dev), torch.from_numpy(tb.PsiD).to(dev),
+                             torch.from_numpy(theta).to(dev), torch.from_numpy(tb.varn).to(dev))
+    torch.cuda.synchronize()
+    m, R, ks, ls = m.cpu().numpy(), R.cpu().numpy(), ks.cpu().numpy(), ls.cpu().numpy()
+    cons = orc.qam_constellation(M)
+    for b in range(B):
+        mo, Ro, ko, lo = orc.posterior_stats(tb.Yd[b], tb.PsiD[b], theta[b], cons, n_tx, varn, hard=hard)
+        assert np.array_equal(ks[b], ko), "hard-decision indices must be bit-exact"
+        assert np.abs(m[b] - mo).max() < 1e-10 * max(1.0, np.abs(mo).max())
+        assert np.abs(R[b] - Ro).max() < 1e-10 * max(1.0, np.abs(Ro).max())
+        if not hard:
+            np.testing.assert_allclose(ls[b], lo, rtol=1e-10, atol=1e-8)
+
+
+def test_estep_zero_theta_is_uniform_posterior(S, orc):
+    """theta = 0 (first iteration of the zero-start scripts): every hypothesis ties; posterior
+    uniform, arg-max = index 0 (np.argmax first-index rule)."""
+    import torch
+
+    N, n_tx, n_rx, M, T_d = 6, 2, 2, 16, 5
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, 4, T_d, 0.1, 2, seed=3, legacy=False)
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=4, T_d=T_d, itera=1)
+    ses = S.DeviceSession(prob, 2)
+    dev = ses.device
+    th = torch.zeros((2, prob.L, n_rx), dtype=torch.complex128, device=dev)
+    m, R, ks, ls = ses.estep(torch.from_numpy(tb.Yd).to(dev), torch.from_numpy(tb.PsiD).to(dev), th,
+                             torch.from_numpy(tb.varn).to(dev))
+    assert int(ks.abs().max()) == 0
+    assert float(m.abs().max()) < 1e-12
+    eye = 10.0 * np.eye(n_tx)
+    assert np.abs(R.cpu().numpy() - eye).max() < 1e-11
+
+
+MSTEP_CASES = [(8, 2, 2, 4, 12, 30), (32, 2, 2, 4, 40, 50), (6, 1, 4, 16, 8, 20), (5, 3, 3, 4, 14, 16),
+               (16, 4, 4, 16, 24, 80), (11, 3, 2, 4, 20, 40), (64, 4, 4, 4, 64, 256)]
+
+
+@pytest.mark.parametrize("case", MSTEP_CASES)
+def test_mstep_matches_oracle(S, orc, case):
+    import torch
+
+    N, n_tx, n_rx, M, T_p, T_d = case
+    B = 2
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, 0.1, B, seed=5, legacy=False)
+    cons = orc.qam_constellation(M)
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=1)
+    # soft statistics from a perturbed theta so R_t is full-rank-ish; computed by the oracle
+    # (for the 64x4x4 case use rank-one statistics of the true symbols to keep the CPU side fast)
+    sm = np.empty((B, T_d, n_tx), np.complex128)
+    sR = np.empty((B, T_d, n_tx, n_tx), np.complex128)
+    for b in range(B):
+        if M ** n_tx <= 4096:
+            sm[b], sR[b], _, _ = orc.posterior_stats(tb.Yd[b], tb.PsiD[b], 0.7 * tb.h[b], cons, n_tx, 2.0)
+        else:
+            sm[b], sR[b] = orc.pilot_stats(tb.Xd[b])
+    ses = S.DeviceSession(prob, B)
+    dev = ses.device
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    theta, status = ses.mstep(t(tb.Yd), t(tb.Yp), t(tb.PsiD), t(tb.PsiP), t(tb.Xp), t(sm), t(sR))
+    torch.cuda.synchronize()
+    theta = theta.cpu().numpy()
+    assert int(status.abs().max()) == 0
+    for b in range(B):
+        mp_, Rp_ = orc.pilot_stats(tb.Xp[b])
+        Gp, Bp = orc.gram_and_rhs(tb.PsiP[b], tb.Yp[b], mp_, Rp_)
+        Gd, Bd = orc.gram_and_rhs(tb.PsiD[b], tb.Yd[b], sm[b], sR[b])
+        ref = np.linalg.solve(Gp + Gd, Bp + Bd)
+        cond = np.linalg.cond(Gp + Gd)
+        assert relerr(theta[b], ref) < max(RTOL, 1e-14 * cond), (relerr(theta[b], ref), cond)
+
+
+def test_mstep_flags_singular_system(S):
+    """T_p + T_d < L: the normal matrix is singular; the trial must be flagged, not poisoned."""
+    import torch
+
+    N, n_tx, n_rx, M, T_p, T_d = 16, 2, 2, 4, 4, 8
+    B = 2
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, 0.1, B, seed=5, legacy=False)
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=1)
+    sm = tb.Xd.conj()
+    sR = tb.Xd.conj()[:, :, :, None] * tb.Xd[:, :, None, :]
+    ses = S.DeviceSession(prob, B)
+    dev = ses.device
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    theta, status = ses.mstep(t(tb.Yd), t(tb.Yp), t(tb.PsiD), t(tb.PsiP), t(tb.Xp), t(sm), t(sR))
+    assert (status.cpu().numpy() != 0).all()
+
+
+# ---------------------------------------------------------------------------
+# whole estimator, reference-signature entry points, golden vectors of the literal reference
+# ---------------------------------------------------------------------------
+
+def _ref_objects(g, n_rx):
+    """Rebuild the reference's Python objects (lists of column vectors, dense Z_p) from a fixture."""
+    Y_d = [g["Yd"][t].reshape(-1, 1) for t in range(g["Yd"].shape[0])]
+    Y_p = [g["Yp"][t].reshape(-1, 1) for t in range(g["Yp"].shape[0])]
+    Z_p = [np.kron(g["Wp"][t][None, :], np.eye(n_rx, dtype=np.complex128)) for t in range(g["Wp"].shape[0])]
+    return Y_d, Y_p, Z_p, g["PsiD"].T.copy()
+
+
+@pytest.mark.parametrize("name", golden_names("soft"))
+def test_em_soft_golden(S, orc, name):
+    meta, g = load_golden(name)
+    n_tx, n_rx, M = int(meta["n_tx"]), int(meta["n_rx"]), int(meta["M"])
+    Y_d, Y_p, Z_p, PsiTilde_td = _ref_objects(g, n_rx)
+    table = orc.hypothesis_table(orc.qam_constellation(M), n_tx)
+    h0 = None if int(meta.get("zero_start", 0)) else g["theta0"].reshape(-1, 1)
+    theta = S.em(Y_d, Y_p, int(meta["T_d"]), int(meta["T_p"]), Z_p, PsiTilde_td, table, M, float(meta["varn"]),
+                 int(meta["itera"]), h0)
+    assert theta.shape == (g["theta_ref"].size, 1)
+    assert relerr(theta.reshape(g["theta_ref"].shape), g["theta_ref"]) < RTOL
+    assert abs(S.nmse(theta, g["h"]) - g["nmse_ref"]) <= 1e-8 * max(1.0, g["nmse_ref"])
+
+
+@pytest.mark.parametrize("name", golden_names("hard"))
+def test_em_hard_golden(S, orc, name):
+    meta, g = load_golden(name)
+    n_tx, n_rx, M = int(meta["n_tx"]), int(meta["n_rx"]), int(meta["M"])
+    T_d, T_p, varn, itera = int(meta["T_d"]), int(meta["T_p"]), float(meta["varn"]), int(meta["itera"])
+    Y_d, Y_p, Z_p, PsiTilde_td = _ref_objects(g, n_rx)
+    table = orc.hypothesis_table(orc.qam_constellation(M), n_tx)
+    X_d = [g["Xd"][t].reshape(-1, 1) for t in range(T_d)]
+    if "llf_ref" in g:
+        theta, llf = S.em_llf(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, table, M, varn, itera, g["theta0"].reshape(-1, 1),
+                              X_d=X_d)
+        assert llf.shape == (itera, 1)
+        np.testing.assert_allclose(llf.reshape(-1), g["llf_ref"], rtol=1e-9)
+    else:
+        theta, X_dest = S.em_ser(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, table, M, varn, itera,
+                                 g["theta0"].reshape(-1, 1))
+        assert np.array_equal(np.vstack(X_dest), g["xdest_ref"])  # bit-exact decisions
+        assert S.ser_as_coded(X_d, X_dest) == g["ser_ref"]
+    assert relerr(theta.reshape(g["theta_ref"].shape), g["theta_ref"]) < RTOL
+
+
+@pytest.mark.parametrize("name", golden_names("multi"))
+def test_multi_detector_golden(S, orc, name):
+    meta, g = load_golden(name)
+    n_tx, n_rx, M = int(meta["n_tx"]), int(meta["n_rx"]), int(meta["M"])
+    T_d, T_p, varn, itera = int(meta["T_d"]), int(meta["T_p"]), float(meta["varn"]), int(meta["itera"])
+    Y_d, Y_p, Z_p, PsiTilde_td = _ref_objects(g, n_rx)
+    table = orc.hypothesis_table(orc.qam_constellation(M), n_tx)
+    h0 = g["theta0"].reshape(-1, 1)
+    th = S.em(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, table, M, varn, itera, h0, h=g["h"], genie_stop=True)
+    assert relerr(th.reshape(g["h"].shape), g["theta_em_ref"]) < RTOL
+    th = S.em_ml(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, table, M, varn, itera, h0, h=g["h"])
+    assert relerr(th.reshape(g["h"].shape), g["theta_ml_ref"]) < RTOL
+
+
+BATCH_CASES = [
+    # N, n_tx, n_rx, M, T_p, T_d, itera, varn, mode
+    (32, 2, 2, 4, 40, 50, 10, 0.1, "soft"),      # shipped config 1, well-posed point
+    (32, 1, 8, 4, 16, 60, 6, 0.1, "soft"),       # shipped config 2 shape
+    (16, 2, 2, 16, 20, 60, 4, 0.4, "soft"),
+    (16, 2, 2, 16, 20, 60, 4, 0.4, "hard"),
+    (10, 3, 3, 4, 24, 40, 4, 0.3, "soft"),
+    (12, 4, 4, 4, 32, 64, 3, 0.2, "soft"),
+    (8, 4, 4, 16, 24, 40, 2, 0.5, "soft"),
+    (8, 4, 4, 16, 24, 40, 2, 0.5, "hard"),
+]
+
+
+@pytest.mark.parametrize("case", BATCH_CASES)
+def test_em_batch_matches_oracle(S, orc, case):
+    N, n_tx, n_rx, M, T_p, T_d, itera, varn, mode = case
+    B = 4
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn, B, seed=42, legacy=False)
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera, mode=mode)
+    res = S.run_host(prob, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, tb.varn, theta0=tb.theta0, h_true=tb.h,
+                     Xd_true=tb.Xd)
+    assert (res.status == 0).all() and (res.iters == itera).all()
+    for b in range(B):
+        ref, tr = orc.em(tb.Yd[b], tb.Yp[b], tb.PsiD[b], tb.PsiP[b], tb.Xp[b], M, varn, itera, theta0=tb.theta0[b],
+                         hard=(mode == "hard"), Xd_true=tb.Xd[b], return_trace=True)
+        assert relerr(res.theta[b], ref) < RTOL
+        assert np.array_equal(res.kstar[b], tr["kstar"])
+        nm = orc.nmse(ref, tb.h[b])
+        assert abs(res.nmse[b] - nm) <= 5e-5 * nm  # 4 significant figures
+        np.testing.assert_allclose(res.llf[b], np.array(tr["llf"]), rtol=1e-8)
+        if mode == "soft":
+            np.testing.assert_allclose(res.lse[b], np.array(tr["lse"]), rtol=1e-9)
+
+
+def test_zero_start_and_shared_status(S, orc):
+    """theta0 = 0 start of the top-level scripts (Proposed_method_NMSEvsTp.py:45)."""
+    N, n_tx, n_rx, M, T_p, T_d, itera, varn = 16, 2, 2, 4, 24, 40, 6, 0.1
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn, 3, seed=9, legacy=False, variant="top_tp")
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera, zero_start=True)
+    res = S.run_host(prob, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, tb.varn, h_true=tb.h)
+    for b in range(3):
+        ref = orc.em(tb.Yd[b], tb.Yp[b], tb.PsiD[b], tb.PsiP[b], tb.Xp[b], M, varn, itera, theta0=None)
+        assert relerr(res.theta[b], ref) < RTOL
+
+
+def test_north_star_size_properties(S):
+    """N=64, 4x4, 16-QAM (K=65536): too slow for the oracle at full size, so check
+    size-independent properties: (a) noiseless data with theta0 = truth is a fixed point of the
+    M-step and decisions equal the transmitted symbols; (b) EM does not increase NMSE from the LS start
+    at high SNR; (c) hard and soft EM agree when posteriors are collapsed."""
+    N, n_tx, n_rx, M, T_p, T_d = 64, 4, 4, 16, 64, 288
+    B = 2
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, 1e-4, B, seed=1, legacy=False)
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=2, mode="soft")
+    res = S.run_host(prob, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, np.full(B, 0.05), theta0=tb.h, h_true=tb.h)
+    assert (res.status == 0).all()
+    k_true = (tb.idx_d * (M ** np.arange(n_tx - 1, -1, -1))).sum(axis=2)
+    assert np.array_equal(res.kstar, k_true.astype(np.int32))
+    assert res.nmse.max() < 1e-6
+    prob_h = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=2, mode="hard")
+    res_h = S.run_host(prob_h, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, np.full(B, 0.05), theta0=tb.h, h_true=tb.h)
+    assert relerr(res_h.theta, res.theta) < 1e-9
