@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- EM channel-estimation trials/s on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--trials-per-step B]
+
+Workload (BASELINE.json configs[1], the north-star size): one NMSE-vs-T_d sweep point of
+Proposed_method_NMSEvsTd.py scaled to N=64 RIS elements, 4x4 MIMO, 16-QAM (K = 65536 joint
+hypotheses per data symbol), T_p=320, T_d=256, 10 EM iterations, soft-decision EM from the LS start,
+varn=0.1 -- an operating point where the LS start is identifiable (T_p >= L=260) and EM improves the
+NMSE ~25x (1.3e-2 -> 5.6e-4, measured); at the reference's T_p=16 the M-step is singular at this L.  A "step" is one batched call of the hot path over
+`B` independent Monte-Carlo trials per GPU; trials are sharded across ranks (disjoint seeds, no
+data-path collective) -> weak scaling.
+
+Prints ONE JSON line (rank 0).  `value` = trials/s with inputs resident in HBM (CUDA-event
+timed, max over ranks); `e2e` = the same through the host-buffer C-ABI entry point
+(pinned host memory -> H2D -> kernels -> D2H inside the timed region).
+`--impl reference` times the CPU restatement of the reference (oracle/em_numpy.py; the
+literal reference is Python that cannot travel and takes hours per trial at this size) on
+the host cores, on the same config/metric/unit.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(N=64, n_tx=4, n_rx=4, M=16, T_p=320, T_d=256, itera=10, varn=0.1, mode="soft")
+PILOT_DESIGN = "top_tp"   # ones row + exp(-j2pi t n/T_p) (Proposed_method_NMSEvsTd.py:86,96); data phases random per trial
+METRIC = "EM channel-estimation trials/sec"
+UNIT = "trials/s"
+
+
+def workload_name(w):
+    return ("nmse_vs_td point: N=%(N)d RIS, %(n_tx)dx%(n_rx)d MIMO, %(M)d-QAM, T_p=%(T_p)d, T_d=%(T_d)d, "
+            "%(itera)d EM iterations, %(mode)s EM, LS start, varn=%(varn)g") % w
+
+
+# ---------------------------------------------------------------------------
+# algorithmic work models (stated in DESIGN.md section 5)
+# ---------------------------------------------------------------------------
+
+def flops_models(w):
+    N1, n_tx, n_rx, M, T_d = w["N"] + 1, w["n_tx"], w["n_rx"], w["M"], w["T_d"]
+    L = N1 * n_tx
+    sq = int(round(M ** 0.5))
+    # hypothesis tree: level s (stream s fixed) costs 5 + 2 s flops per node at that level, every
+    # deepest node pays the separable leaf scan (3 sqrt(M) + 2 flops)
+    enum, count = 0.0, 1.0
+    for s in range(n_tx - 1, 0, -1):
+        count *= M
+        enum += count * (5 + 2 * s)
+    enum += count * (3 * sq + 2)
+    nr = max(n_rx, n_tx)
+    return dict(
+        enum=T_d * enum,                                               # per trial-iteration
+        heff_qr=T_d * (8.0 * N1 * n_tx * n_rx + 16.0 * n_tx * n_tx * nr),
+        gram=4.0 * T_d * L * (L + 1),                                  # SURVEY 8d F_G
+        chol=4.0 * L ** 3 / 3.0 + 8.0 * n_rx * L * L,                  # SURVEY 8d F_S
+        rhs=8.0 * T_d * L * (n_rx + 1),                                # SURVEY 8d F_B
+        survey_estep=T_d * (float(M) ** n_tx * (2 * n_tx * n_rx + 4 * n_rx + 3 + 4 * n_tx + 2 * n_tx * (n_tx + 1))
+                            + 8.0 * N1 * n_tx * n_rx + 8.0 * n_tx * M * n_rx),  # SURVEY 8d F_E (naive enumeration)
+    )
+
+
+def bytes_models(w):
+    N1, n_tx, n_rx, T_d = w["N"] + 1, w["n_tx"], w["n_rx"], w["T_d"]
+    rec = n_tx * (n_tx + 1) + 2 * n_tx + 2
+    return dict(heff_qr=T_d * (16.0 * (N1 + n_rx) + 8.0 * rec))        # psi row + y in, QR record out
+
+
+# ---------------------------------------------------------------------------
+# clocks sampling
+# ---------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------
+# reference arm (CPU)
+# ---------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import cpu_bench
+
+    w = WORKLOAD
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        r = cpu_bench.time_sample(w["N"], w["n_tx"], w["n_rx"], w["M"], w["T_p"], w["T_d"], w["varn"], w["itera"],
+                                  sample_iters=1, workers=None, hard=(w["mode"] == "hard"), seed=1000 + 97 * i)
+        if i >= args.warmup:
+            vals.append(r)
+        last = r
+    tot_slices = sum(r["cores"] for r in vals) / float(w["itera"])     # trial-equivalents processed
+    tot_time = sum(r["slowest_worker_s"] for r in vals)
+    value = tot_slices / tot_time
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * tot_time / max(1, len(vals)), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=workload_name(w), **w),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=last["cores"], kind="port", sample=last["sample"]),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# our arm (GPU)
+# ---------------------------------------------------------------------------
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as tdist
+
+    import sbce
+    from sbce import dist as sdist, engine, signal_model
+
+    rank, world, local = sdist.init_from_env("nccl")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sbce._lib.require_device()
+
+    w = dict(WORKLOAD)
+    B = args.trials_per_step
+    prob = engine.Problem(N=w["N"], n_tx=w["n_tx"], n_rx=w["n_rx"], M=w["M"], T_p=w["T_p"], T_d=w["T_d"],
+                          itera=w["itera"], mode=w["mode"])
+    # synthetic inputs, generated once by numpy on the host (disjoint seed per rank)
+    tb = signal_model.generate_batch(w["N"], w["n_tx"], w["n_rx"], w["M"], w["T_p"], w["T_d"], w["varn"], B,
+                                     seed=20260 + 7919 * rank, legacy=False, variant=PILOT_DESIGN)
+    host_in = dict(Yd=tb.Yd, Yp=tb.Yp, PsiD=tb.PsiD, PsiP=tb.PsiP, Xp=tb.Xp, theta0=tb.theta0, h_true=tb.h)
+    t_dev = {k: torch.from_numpy(v).to(dev) for k, v in host_in.items()}
+    varn_dev = torch.from_numpy(tb.varn).to(dev)
+    input_bytes = sum(v.nbytes for v in host_in.values()) + tb.varn.nbytes
+
+    ses = engine.DeviceSession(prob, B, device=dev)
+    out = ses.alloc_outputs(B, llf=False, lse=True, nmse=True, kstar=True)
+
+    def step():
+        ses.run(t_dev["Yd"], t_dev["Yp"], t_dev["PsiD"], t_dev["PsiP"], t_dev["Xp"], varn_dev,
+                theta0=t_dev["theta0"], h_true=t_dev["h_true"], out=out)
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    fp64_peak = engine.fp64_peak_tflops()          # live DFMA microbenchmark (no FP64 entry in MEASURED_PEAKS.json)
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    engine.launch_count(reset=True)
+    engine.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    phases = engine.profile_end()
+    launches = engine.launch_count()
+    clocks = sampler.stop()
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        tdist.all_reduce(tms, op=tdist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # sanity: the timed work produced valid estimates
+    nm = out.nmse.cpu().numpy()
+    st = out.status.cpu().numpy()
+    nmse_mean = float(nm[st == 0].mean()) if (st == 0).any() else float("nan")
+    nmse_init = float(np.mean([sbce.nmse(tb.theta0[i], tb.h[i]) for i in range(min(B, 64))]))
+
+    # ---- end-to-end through the host-buffer C-ABI entry point, pinned host memory
+    pin = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in host_in.items()}
+    varn_pin = torch.from_numpy(tb.varn).pin_memory().numpy()
+    hout = engine.alloc_host_outputs(prob, B, want=("kstar", "lse", "nmse", "iters", "status"), pinned=True)
+    d2h_bytes = sum(getattr(hout, k).nbytes for k in ("theta", "kstar", "lse", "nmse", "iters", "status"))
+
+    def e2e_step():
+        engine.run_host(prob, pin["Yd"], pin["Yp"], pin["PsiD"], pin["PsiP"], pin["Xp"], varn_pin,
+                        theta0=pin["theta0"], h_true=pin["h_true"], device=local, out=hout)
+
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()          # synchronous: returns after the D2H copies completed
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    te = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        tdist.all_reduce(te, op=tdist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            tdist.barrier()
+            tdist.destroy_process_group()
+        return 0
+
+    # ---- per-kernel roofline from the CUDA-event phase timers recorded inside the timed region
+    fm, bm = flops_models(w), bytes_models(w)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    total_phase_ms = sum(v[0] for v in phases.values())
+    kernels = {}
+    for name, (pms, cnt) in phases.items():
+        if cnt == 0:
+            continue
+        avg_s = pms * 1e-3 / cnt
+        k = dict(ms_total=pms, launches=cnt, share=pms / total_phase_ms, avg_launch_ms=1e3 * avg_s)
+        if name in fm:
+            k["tflops"] = fm[name] * B / avg_s / 1e12
+            k["frac_fp64_peak"] = k["tflops"] / fp64_peak if fp64_peak > 0 else None
+        if name in bm:
+            k["gbs"] = bm[name] * B / avg_s / 1e9
+            k["frac_hbm_peak"] = k["gbs"] / hbm_peak
+        kernels[name] = k
+    top = max((n for n in kernels if n in fm), key=lambda n: kernels[n]["ms_total"])
+    roofline = dict(bound="fp64", kernel=top, achieved=kernels[top]["tflops"], peak=fp64_peak, unit="TFLOP/s",
+                    frac=kernels[top]["frac_fp64_peak"], traffic=None, share_of_step=kernels[top]["share"],
+                    peak_source="live DFMA micro-benchmark in libsbce (2 flop/FMA); MEASURED_PEAKS.json has no FP64 entry",
+                    flops_per_launch=fm[top] * B,
+                    note="FP64 vector pipe bound (tcgen05 has no FP64 kind); algorithmic flop models in DESIGN.md section 5")
+    if "heff_qr" in kernels and "gbs" in kernels["heff_qr"]:
+        roofline["hbm_side"] = dict(kernel="heff_qr", achieved=kernels["heff_qr"]["gbs"], peak=hbm_peak, unit="GB/s",
+                                    frac=kernels["heff_qr"]["frac_hbm_peak"], peak_source=hbm_src)
+    if "enum" in kernels:
+        roofline["estep_survey_model_tflops"] = fm["survey_estep"] * B / (kernels["enum"]["avg_launch_ms"] * 1e-3) / 1e12
+
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_bench
+
+        r = cpu_bench.time_sample(w["N"], w["n_tx"], w["n_rx"], w["M"], w["T_p"], w["T_d"], w["varn"], w["itera"],
+                                  sample_iters=1, workers=None, hard=False)
+        cpu = dict(value=r["trials_per_s"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
+                   seconds=r["seconds"])
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic",
+                config=dict(workload=workload_name(w), trials_per_step_per_gpu=B, pilot_design=PILOT_DESIGN, enumeration="full (all M^n_tx hypotheses)",
+                            l2="inputs (%.0f MB per GPU) larger than the 126 MB L2" % (input_bytes / 1e6), **w),
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(input_bytes), d2h_bytes_per_step=int(d2h_bytes),
+                         steps=e2e_steps),
+                gpu_launches=int(launches), clocks=clocks, roofline=roofline, kernels=kernels, cpu_baseline=cpu,
+                check=dict(nmse_mean=nmse_mean, nmse_ls_start=nmse_init, flagged_trials=int((st != 0).sum())))
+    print(json.dumps(line))
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--trials-per-step", type=int, default=592)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

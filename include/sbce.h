@@ -149,6 +149,21 @@ int sbce_accumulate_nmse(const double* nmse, const int32_t* status, int32_t batc
  * FMA), used as the roofline denominator for the FP64-bound kernels. */
 int sbce_measure_fp64_peak(double* tflops, double* seconds);
 
+/* Per-phase device timing (CUDA events on the launch stream around every phase of
+ * sbce_em_batch), used by bench.py for the per-kernel roofline numbers.
+ * sbce_profile_begin() arms it; sbce_profile_end() disarms, synchronises and returns
+ * the summed milliseconds and the number of timed launches per phase. */
+#define SBCE_PHASE_SETUP 0   /* state init + pilot normal equations (once per call)      */
+#define SBCE_PHASE_HEFF_QR 1 /* effective channel + Householder QR (one lane per symbol) */
+#define SBCE_PHASE_ENUM 2    /* hypothesis-tree posterior sweep (one warp per symbol)    */
+#define SBCE_PHASE_GRAM 3    /* Hermitian normal-matrix build                            */
+#define SBCE_PHASE_RHS 4     /* right-hand side rows + padding                           */
+#define SBCE_PHASE_CHOL 5    /* blocked Cholesky + triangular solves                     */
+#define SBCE_PHASE_METRICS 6 /* per-iteration bookkeeping, LLF, NMSE                     */
+#define SBCE_N_PHASES 7
+int sbce_profile_begin(void);
+int sbce_profile_end(double* ms_per_phase, int64_t* spans_per_phase, int32_t n_phases);
+
 /* Number of kernels this library launched since the last reset (for bench.py's
  * gpu_launches claim). */
 int64_t sbce_launch_count(int32_t reset);

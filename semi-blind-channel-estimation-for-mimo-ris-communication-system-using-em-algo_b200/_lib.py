@@ -39,7 +39,9 @@ class Io(C.Structure):
 # every symbol include/sbce.h declares; tests assert the library exports all of them
 EXPORTS = ["sbce_version", "sbce_error_string", "sbce_device_count", "sbce_workspace_bytes", "sbce_em_batch",
            "sbce_em_batch_host", "sbce_estep", "sbce_mstep", "sbce_accumulate_nmse", "sbce_measure_fp64_peak",
-           "sbce_launch_count"]
+           "sbce_launch_count", "sbce_profile_begin", "sbce_profile_end"]
+
+PHASES = ["setup", "heff_qr", "enum", "gram", "rhs", "chol", "metrics"]
 
 _lib = None
 
@@ -66,6 +68,7 @@ def load():
                                C.c_void_p, C.c_size_t, C.c_void_p]
     lib.sbce_accumulate_nmse.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.sbce_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.sbce_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
     lib.sbce_launch_count.restype = C.c_int64
     lib.sbce_launch_count.argtypes = [C.c_int32]
     _lib = lib

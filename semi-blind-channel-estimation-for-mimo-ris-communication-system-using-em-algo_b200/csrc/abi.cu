@@ -2,6 +2,7 @@
 // carve-up, chunking of the batch, and the kernel schedule of the EM loop.
 #include <atomic>
 #include <mutex>
+#include <vector>
 #include <stdio.h>
 #include <string.h>
 
@@ -11,6 +12,32 @@ namespace sbce {
 
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional per-phase CUDA-event timing (bench.py's roofline numbers) --------------------------
+// Events are recorded on the launch stream around every phase while profiling is on; the cost is one
+// cudaEventRecord pair per phase launch.  sbce_profile_end() synchronises and sums the intervals.
+struct PhaseSpan { int phase; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<PhaseSpan> g_spans;
+static std::vector<cudaEvent_t> g_event_pool;
+static std::mutex g_prof_mu;
+
+static cudaEvent_t prof_event() {
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct PhaseScope {
+    bool on; int phase; cudaStream_t s; cudaEvent_t a;
+    PhaseScope(int ph, cudaStream_t st) : on(g_prof_on), phase(ph), s(st), a(nullptr) {
+        if (on) { a = prof_event(); cudaEventRecord(a, s); }
+    }
+    ~PhaseScope() {
+        if (on) { cudaEvent_t b = prof_event(); cudaEventRecord(b, s); g_spans.push_back({phase, a, b}); }
+    }
+};
 
 static int make_dims(const sbce_cfg* c, Dims* d) {
     if (!c) return SBCE_E_NULL;
@@ -75,29 +102,57 @@ static int estep_dispatch(const Dims& d, int nb, const double* Yd, const double*
                           const double* varn, const int32_t* active, Workspace& ws, double* stat_m, double* stat_R,
                           int32_t* kstar, double* lse_sym, cudaStream_t s) {
     if (d.mode == SBCE_MODE_SOFT || d.mode == SBCE_MODE_HARD) {
-        CK(launch_estep(d, nb, Yd, PsiD, theta, varn, active, ws.qr, stat_m, stat_R, kstar, lse_sym, s));
+        {
+            PhaseScope ps(SBCE_PHASE_HEFF_QR, s);
+            CK(launch_heff_qr(d, nb, Yd, PsiD, theta, active, ws.qr, s));
+        }
+        {
+            PhaseScope ps(SBCE_PHASE_ENUM, s);
+            CK(launch_enum(d, nb, ws.qr, varn, active, stat_m, stat_R, kstar, lse_sym, s));
+        }
     } else {
+        PhaseScope ps(SBCE_PHASE_ENUM, s);
         CK(launch_pm_stats(d, nb, Yd, PsiD, theta, varn, active, stat_m, stat_R, s));
     }
     return 0;
 }
 
 static int em_chunk(const Dims& d, int nb, const sbce_io& io, Workspace& ws, cudaStream_t s) {
-    CK(launch_init_state(d, nb, io.theta0, io.theta, ws.active, ws.stat, io.iters, io.llf, io.lse, s));
-    // pilot part of the normal equations, once (the reference recomputes it every iteration:
-    // Proposed_method_NMSEvsTp.py:63-65)
-    CK(launch_pilot_stats(d, nb, io.Xp, ws.pil_m, ws.pil_R, s));
-    CK(launch_gram(d, nb, io.PsiP, d.T_p, io.Yp, ws.pil_m, ws.pil_R, nullptr, ws.Gp, nullptr, s));
+    {
+        PhaseScope ps(SBCE_PHASE_SETUP, s);
+        CK(launch_init_state(d, nb, io.theta0, io.theta, ws.active, ws.stat, io.iters, io.llf, io.lse, s));
+        // pilot part of the normal equations, once (the reference recomputes it every iteration:
+        // Proposed_method_NMSEvsTp.py:63-65)
+        CK(launch_pilot_stats(d, nb, io.Xp, ws.pil_m, ws.pil_R, s));
+        CK(launch_gram(d, nb, io.PsiP, d.T_p, ws.pil_R, nullptr, ws.Gp, nullptr, s));
+        CK(launch_rhs_pad(d, nb, io.PsiP, d.T_p, io.Yp, ws.pil_m, nullptr, ws.Gp, nullptr, s));
+    }
     for (int l = 0; l < d.itera; ++l) {
         int rc = estep_dispatch(d, nb, io.Yd, io.PsiD, io.theta, io.varn, ws.active, ws, ws.stat_m, ws.stat_R,
                                 io.kstar, ws.lse_sym, s);
         if (rc) return rc;
-        CK(launch_gram(d, nb, io.PsiD, d.T_d, io.Yd, ws.stat_m, ws.stat_R, ws.Gp, ws.G, ws.active, s));
-        CK(launch_chol_solve(d, nb, ws.G, io.theta, ws.active, ws.stat, s));
-        CK(launch_after_iteration(d, nb, l, io.theta, io.h_true, io.Yp, io.Yd, io.PsiP, io.PsiD, io.Xp, io.Xd_true,
-                                  io.varn, ws.lse_sym, ws.active, io.iters, io.llf, io.lse, s));
+        {
+            PhaseScope ps(SBCE_PHASE_GRAM, s);
+            CK(launch_gram(d, nb, io.PsiD, d.T_d, ws.stat_R, ws.Gp, ws.G, ws.active, s));
+        }
+        {
+            PhaseScope ps(SBCE_PHASE_RHS, s);
+            CK(launch_rhs_pad(d, nb, io.PsiD, d.T_d, io.Yd, ws.stat_m, ws.Gp, ws.G, ws.active, s));
+        }
+        {
+            PhaseScope ps(SBCE_PHASE_CHOL, s);
+            CK(launch_chol_solve(d, nb, ws.G, io.theta, ws.active, ws.stat, s));
+        }
+        {
+            PhaseScope ps(SBCE_PHASE_METRICS, s);
+            CK(launch_after_iteration(d, nb, l, io.theta, io.h_true, io.Yp, io.Yd, io.PsiP, io.PsiD, io.Xp,
+                                      io.Xd_true, io.varn, ws.lse_sym, ws.active, io.iters, io.llf, io.lse, s));
+        }
     }
-    CK(launch_final_metrics(d, nb, io.theta, io.h_true, ws.stat, io.nmse, io.status, s));
+    {
+        PhaseScope ps(SBCE_PHASE_METRICS, s);
+        CK(launch_final_metrics(d, nb, io.theta, io.h_true, ws.stat, io.nmse, io.status, s));
+    }
     return 0;
 }
 
@@ -249,9 +304,10 @@ int sbce_mstep(const sbce_cfg* cfg, const sbce_io* io, const double* stat_m, con
         const size_t sb = (size_t)b0 * d.T_d;
         CK(cudaMemsetAsync(ws.stat, 0, (size_t)nb * 4, s));
         CK(launch_pilot_stats(d, nb, o.Xp, ws.pil_m, ws.pil_R, s));
-        CK(launch_gram(d, nb, o.PsiP, d.T_p, o.Yp, ws.pil_m, ws.pil_R, nullptr, ws.Gp, nullptr, s));
-        CK(launch_gram(d, nb, o.PsiD, d.T_d, o.Yd, stat_m + sb * d.n_tx * 2, stat_R + sb * d.n_tx * d.n_tx * 2, ws.Gp,
-                       ws.G, nullptr, s));
+        CK(launch_gram(d, nb, o.PsiP, d.T_p, ws.pil_R, nullptr, ws.Gp, nullptr, s));
+        CK(launch_rhs_pad(d, nb, o.PsiP, d.T_p, o.Yp, ws.pil_m, nullptr, ws.Gp, nullptr, s));
+        CK(launch_gram(d, nb, o.PsiD, d.T_d, stat_R + sb * d.n_tx * d.n_tx * 2, ws.Gp, ws.G, nullptr, s));
+        CK(launch_rhs_pad(d, nb, o.PsiD, d.T_d, o.Yd, stat_m + sb * d.n_tx * 2, ws.Gp, ws.G, nullptr, s));
         CK(launch_chol_solve(d, nb, ws.G, theta_out + (size_t)b0 * d.L * d.n_rx * 2, nullptr, ws.stat, s));
         if (status) CK(cudaMemcpyAsync(status + b0, ws.stat, (size_t)nb * 4, cudaMemcpyDeviceToDevice, s));
     }
@@ -266,6 +322,34 @@ int sbce_accumulate_nmse(const double* nmse, const int32_t* status, int32_t batc
 
 int sbce_measure_fp64_peak(double* tflops, double* seconds) {
     CK(run_fp64_peak(tflops, seconds));
+    return 0;
+}
+
+int sbce_profile_begin(void) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    for (auto& sp : g_spans) { g_event_pool.push_back(sp.a); g_event_pool.push_back(sp.b); }
+    g_spans.clear();
+    g_prof_on = true;
+    return 0;
+}
+
+int sbce_profile_end(double* ms_per_phase, int64_t* spans_per_phase, int32_t n_phases) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    g_prof_on = false;
+    if (!ms_per_phase || n_phases < 1) return SBCE_E_NULL;
+    for (int i = 0; i < n_phases; ++i) { ms_per_phase[i] = 0.0; if (spans_per_phase) spans_per_phase[i] = 0; }
+    for (auto& sp : g_spans) {
+        CK(cudaEventSynchronize(sp.b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        if (sp.phase >= 0 && sp.phase < n_phases) {
+            ms_per_phase[sp.phase] += ms;
+            if (spans_per_phase) spans_per_phase[sp.phase] += 1;
+        }
+        g_event_pool.push_back(sp.a);
+        g_event_pool.push_back(sp.b);
+    }
+    g_spans.clear();
     return 0;
 }
 

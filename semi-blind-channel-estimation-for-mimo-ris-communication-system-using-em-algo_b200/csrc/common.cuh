@@ -94,12 +94,15 @@ size_t carve_workspace(const Dims& d, int nb, void* base, Workspace* ws);
 // ---- launchers (one translation unit each) --------------------------------
 // E-step side (estep.cu)
 cudaError_t launch_pilot_stats(const Dims& d, int nb, const double* Xp, double* pil_m, double* pil_R, cudaStream_t s);
-cudaError_t launch_estep(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
-                         const double* varn, const int32_t* active, double* qr, double* stat_m, double* stat_R,
-                         int32_t* kstar, double* lse_sym, cudaStream_t s);
+cudaError_t launch_heff_qr(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
+                           const int32_t* active, double* qr, cudaStream_t s);
+cudaError_t launch_enum(const Dims& d, int nb, const double* qr, const double* varn, const int32_t* active,
+                        double* stat_m, double* stat_R, int32_t* kstar, double* lse_sym, cudaStream_t s);
 // M-step side (mstep.cu)
-cudaError_t launch_gram(const Dims& d, int nb, const double* Psi, int T, const double* Y, const double* sm,
-                        const double* sR, const double* Ginit, double* Gout, const int32_t* active, cudaStream_t s);
+cudaError_t launch_gram(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Ginit,
+                        double* Gout, const int32_t* active, cudaStream_t s);
+cudaError_t launch_rhs_pad(const Dims& d, int nb, const double* Psi, int T, const double* Y, const double* sm,
+                           const double* Ginit, double* Gout, const int32_t* active, cudaStream_t s);
 cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
                               cudaStream_t s);
 // metrics (metrics.cu)

@@ -167,36 +167,38 @@ __global__ void __launch_bounds__(128) k_heff_qr(Dims d, const cplx* __restrict_
 // ---------------------------------------------------------------------------
 // 2. hypothesis-tree enumeration, one warp per symbol
 // ---------------------------------------------------------------------------
-constexpr double SBCE_THR = 64.0;  // nodes whose best leaf is > THR*varn^2 above the running min weigh < e^-64
+constexpr double SBCE_THR = 64.0;  // nodes whose best leaf is > THR*varn^2 above the incumbent weigh < e^-64
+constexpr int ENUM_QCAP = 1024;    // per-warp candidate queue (node codes)
 
-template <int NTX, int SQM, bool HARD>
-struct Enum {
+template <int NTX, int SQM>
+struct EnumT {
     static constexpr int M = SQM * SQM;
     static constexpr int BITS = (SQM == 2 ? 2 : (SQM == 4 ? 4 : 6));
+    static constexpr int HB = BITS / 2;
     static constexpr int NODE_STREAMS = NTX - 1;
     static constexpr int PLWANT = (5 + BITS - 1) / BITS;  // prefix streams so that M^PL >= 32
     static constexpr int PL = NODE_STREAMS < PLWANT ? NODE_STREAMS : PLWANT;
     static constexpr int NPREF = 1 << (BITS * PL);
     static constexpr int NPAIR = NTX * (NTX - 1) / 2;
     static constexpr int NPAIR1 = NPAIR > 0 ? NPAIR : 1;
-    static constexpr int TAB_DOUBLES = 2 * NPAIR1 * M + NTX * SQM;  // per warp
-
-    // per-lane state
-    const cplx* tab;    // [pair][m]  R_is * c_m, pair(i<s) = s(s-1)/2 + i
-    const double* g;    // [s][a]     R_ss * pam_a
-    double s2, inv_s2, thr;
-    double ref;         // running reference d2 (max-subtraction point)
-    double best;
-    int bestk;
-    double S;
-    double mre[NTX], mim[NTX], Rd[NTX];
-    cplx Ro[NPAIR1];
+    static constexpr int NACC = 1 + 3 * NTX + 2 * NPAIR;  // S, m (re,im), R diag, R upper (re,im)
+    // per-warp shared block (doubles): tables, PAM levels, ytilde, c0, accumulators, aref, then ints
+    static constexpr int O_TAB = 0;
+    static constexpr int O_G = O_TAB + 2 * NPAIR1 * M;
+    static constexpr int O_YT = O_G + NTX * SQM;
+    static constexpr int O_C0 = O_YT + 2 * NTX;
+    static constexpr int O_ACC = O_C0 + 1;
+    static constexpr int O_AREF = O_ACC + NACC;
+    static constexpr int O_S2 = O_AREF + 1;     // inv_s2
+    static constexpr int O_CNT = O_S2 + 1;      // int counter lives in this double slot
+    static constexpr int O_Q = O_CNT + 1;       // ENUM_QCAP ints = ENUM_QCAP/2 doubles
+    static constexpr int WS_DOUBLES = ((O_Q + ENUM_QCAP / 2) + 1) & ~1;
 
     __device__ __forceinline__ static double pam(int a) { return (double)(2 * a - SQM + 1); }
-    __device__ __forceinline__ static cplx cval(int m) { return mk(pam(m & (SQM - 1)), pam(m >> (BITS / 2))); }
+    __device__ __forceinline__ static cplx cval(int m) { return mk(pam(m & (SQM - 1)), pam(m >> HB)); }
     __device__ __forceinline__ static int pair(int i, int s) { return s * (s - 1) / 2 + i; }
 
-    // nearest PAM level to v on axis with levels gs[0..SQM), first index on ties; returns index, writes dist^2
+    // nearest PAM level to v among gs[0..SQM) (increasing), first index on ties; dist = squared distance
     __device__ __forceinline__ static int slice(double v, const double* gs, double& dist) {
         int a = 0;
         double e = v - gs[0];
@@ -204,143 +206,246 @@ struct Enum {
 #pragma unroll
         for (int q = 1; q < SQM; ++q) {
             e = v - gs[q];
-            double dq = e * e;
+            const double dq = e * e;
             if (dq < dist) { dist = dq; a = q; }
         }
         return a;
     }
 
-    __device__ __forceinline__ void rescale(double f) {
-        S *= f;
-#pragma unroll
-        for (int j = 0; j < NTX; ++j) { mre[j] *= f; mim[j] *= f; Rd[j] *= f; }
-#pragma unroll
-        for (int q = 0; q < NPAIR; ++q) Ro[q] = cscale(Ro[q], f);
+    // distance from v to the nearest level of the symmetric PAM set {+-r, +-3r, ...}: fold |v| around the
+    // midpoints (for 4 levels: ||v| - 2r| - r), no comparisons, 1 + log2(SQM/2) subtractions
+    __device__ __forceinline__ static double fold(double v, double r) {
+        double a = fabs(v);
+        if (SQM == 8) a = fabs(a - 4.0 * r);
+        if (SQM >= 4) a = fabs(a - 2.0 * r);
+        return a - r;
     }
+};
 
-    // all M leaves of the node whose residual on row 0 is t0 and whose partial distance is base
-    __device__ __forceinline__ void leaf(cplx t0, double base, int kpart) {
-        const double* g0 = g;  // stream 0 levels
-        // best leaf: PAM levels are symmetric, compare |v| with the positive half
-        const double aI = fabs(t0.x), aQ = fabs(t0.y);
-        double e = aI - g0[SQM / 2];
-        double minI = e * e;
-        e = aQ - g0[SQM / 2];
-        double minQ = e * e;
+// Cooperative, out-of-line processing of the queued candidate nodes of one symbol: every lane takes
+// queue entries round-robin, rebuilds the node's residuals from its code, sums its M leaves in closed
+// form (separable in-phase / quadrature PAM sums) and the warp adds the result to the shared
+// accumulators, kept relative to the reference distance `aref` (rescaled when the incumbent improves).
+template <int NTX, int SQM>
+__device__ __noinline__ void enum_flush(double* ws, double warp_best) {
+    typedef EnumT<NTX, SQM> E;
+    constexpr int M = E::M;
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    int* cntp = (int*)(ws + E::O_CNT);
+    const int n = min(*cntp, ENUM_QCAP);
+    const int* q = (const int*)(ws + E::O_Q);
+    const cplx* tab = (const cplx*)(ws + E::O_TAB);
+    const double* g = ws + E::O_G;
+    const double inv_s2 = ws[E::O_S2];
+    double aref = ws[E::O_AREF];
+    if (warp_best < aref) {
+        const double f = exp((warp_best - aref) * inv_s2);  // aref = +inf initially -> f = 0
+        for (int i = lane; i < E::NACC; i += 32) ws[E::O_ACC + i] *= f;
+        aref = warp_best;
+    }
+    // one queue entry per lane per round; the warp reduces every statistic right away (rare path: keep
+    // the register footprint small so that it does not limit the occupancy of the scan loop)
+    double* A = ws + E::O_ACC;
+    auto radd = [&](int idx, double v) {
+        v = warp_sum(v);
+        if (lane == 0) A[idx] += v;
+    };
+    for (int e0 = 0; e0 < n; e0 += 32) {
+        const int e = e0 + lane;
+        const bool have = e < n;
+        const int code = have ? q[e] : 0;
+        cplx t0;
+        double base = ws[E::O_C0];
+        {
+            cplx acc[NTX];
 #pragma unroll
-        for (int q = SQM / 2 + 1; q < SQM; ++q) {
-            e = aI - g0[q];
-            minI = fmin(minI, e * e);
-            e = aQ - g0[q];
-            minQ = fmin(minQ, e * e);
-        }
-        const double nodemin = base + minI + minQ;
-        if (nodemin <= best) {  // rare: resolve the exact leaf and its hypothesis index
-            double dI, dQ;
-            const int iI = slice(t0.x, g0, dI), iQ = slice(t0.y, g0, dQ);
-            const double val = base + dI + dQ;
-            const int k = kpart + ((iQ * SQM + iI) << (BITS * (NTX - 1)));
-            if (val < best || (val == best && k < bestk)) { best = val; bestk = k; }
-        }
-        if (HARD) return;
-        if (nodemin - ref <= thr) {  // rare at operating SNRs: the node carries visible posterior mass
-            double W;
-            if (nodemin < ref) {
-                rescale(exp((nodemin - ref) * inv_s2));
-                ref = nodemin;
-                W = 1.0;
-            } else {
-                W = exp((ref - nodemin) * inv_s2);
+            for (int i = 0; i < NTX; ++i) acc[i] = mk(ws[E::O_YT + 2 * i], ws[E::O_YT + 2 * i + 1]);
+#pragma unroll
+            for (int s = NTX - 1; s >= 1; --s) {
+                const int m = (code >> (E::BITS * (NTX - 1 - s))) & (M - 1);
+                const double eI = acc[s].x - g[s * SQM + (m & (SQM - 1))];
+                const double eQ = acc[s].y - g[s * SQM + (m >> E::HB)];
+                base += fma(eI, eI, eQ * eQ);
+#pragma unroll
+                for (int i = 0; i < NTX; ++i)
+                    if (i < s) acc[i] = csub(acc[i], tab[E::pair(i, s) * M + m]);
             }
-            double EI = 0, A1 = 0, A2 = 0, EQ = 0, B1 = 0, B2 = 0;
+            t0 = acc[0];
+        }
+        double minI = 1e300, minQ = 1e300;
 #pragma unroll
-            for (int q = 0; q < SQM; ++q) {
-                const double pq = pam(q);
-                double eI = t0.x - g0[q];
-                double wI = exp((minI - eI * eI) * inv_s2);
-                EI += wI; A1 = fma(pq, wI, A1); A2 = fma(pq * pq, wI, A2);
-                double eQ = t0.y - g0[q];
-                double wQ = exp((minQ - eQ * eQ) * inv_s2);
-                EQ += wQ; B1 = fma(pq, wQ, B1); B2 = fma(pq * pq, wQ, B2);
-            }
-            const double E0 = W * EI * EQ;
-            const cplx F0 = mk(W * A1 * EQ, -W * EI * B1);  // sum e conj(x_0)
-            const double Q0 = W * (A2 * EQ + EI * B2);      // sum e |x_0|^2
-            S += E0;
-            mre[0] += F0.x; mim[0] += F0.y; Rd[0] += Q0;
-            cplx xs[NTX];
+        for (int a = 0; a < SQM; ++a) {
+            const double eI = t0.x - g[a], eQ = t0.y - g[a];
+            minI = fmin(minI, eI * eI);
+            minQ = fmin(minQ, eQ * eQ);
+        }
+        const double W = have ? exp((aref - (base + minI + minQ)) * inv_s2) : 0.0;
+        double EI = 0, A1 = 0, A2 = 0, EQ = 0, B1 = 0, B2 = 0;
+#pragma unroll 1
+        for (int a = 0; a < SQM; ++a) {
+            const double pq = E::pam(a);
+            const double eI = t0.x - g[a], eQ = t0.y - g[a];
+            const double wI = exp((minI - eI * eI) * inv_s2), wQ = exp((minQ - eQ * eQ) * inv_s2);
+            EI += wI; A1 = fma(pq, wI, A1); A2 = fma(pq * pq, wI, A2);
+            EQ += wQ; B1 = fma(pq, wQ, B1); B2 = fma(pq * pq, wQ, B2);
+        }
+        const double E0 = W * EI * EQ;
+        const cplx F0 = mk(W * A1 * EQ, -W * EI * B1);  // sum over leaves of e * conj(x_0)
+        const double Q0 = W * (A2 * EQ + EI * B2);      // sum over leaves of e * |x_0|^2
+        radd(0, E0);
+        radd(1, F0.x);
+        radd(1 + NTX, F0.y);
+        radd(1 + 2 * NTX, Q0);
 #pragma unroll
-            for (int s = 1; s < NTX; ++s) xs[s] = cval((kpart >> (BITS * (NTX - 1 - s))) & (M - 1));
+        for (int s = 1; s < NTX; ++s) {
+            const cplx xs = E::cval((code >> (E::BITS * (NTX - 1 - s))) & (M - 1));
+            radd(1 + s, E0 * xs.x);
+            radd(1 + NTX + s, -E0 * xs.y);
+            radd(1 + 2 * NTX + s, E0 * cnorm2(xs));
+            const cplx v = cmul(F0, xs);  // conj(x_0) x_s summed over the leaves
+            radd(1 + 3 * NTX + 2 * E::pair(0, s), v.x);
+            radd(1 + 3 * NTX + 2 * E::pair(0, s) + 1, v.y);
 #pragma unroll
-            for (int s = 1; s < NTX; ++s) {
-                mre[s] = fma(E0, xs[s].x, mre[s]);
-                mim[s] = fma(-E0, xs[s].y, mim[s]);
-                Rd[s] = fma(E0, cnorm2(xs[s]), Rd[s]);
-                cfma(Ro[pair(0, s)], F0, xs[s]);
-#pragma unroll
-                for (int i = 1; i < s; ++i) {
-                    cplx cx = cmulc(xs[s], xs[i]);  // conj(x_i) x_s
-                    Ro[pair(i, s)].x = fma(E0, cx.x, Ro[pair(i, s)].x);
-                    Ro[pair(i, s)].y = fma(E0, cx.y, Ro[pair(i, s)].y);
+            for (int i = 1; i < NTX; ++i)
+                if (i < s) {
+                    const cplx xi = E::cval((code >> (E::BITS * (NTX - 1 - i))) & (M - 1));
+                    const cplx cx = cmulc(xs, xi);  // conj(x_i) x_s
+                    radd(1 + 3 * NTX + 2 * E::pair(i, s), E0 * cx.x);
+                    radd(1 + 3 * NTX + 2 * E::pair(i, s) + 1, E0 * cx.y);
+                }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        ws[E::O_AREF] = aref;
+        *cntp = 0;
+    }
+    __syncwarp();
+}
+
+template <int NTX, int SQM, bool HARD>
+struct Scan {
+    typedef EnumT<NTX, SQM> E;
+    static constexpr int M = E::M;
+    double* ws;
+    const cplx* tab;
+    const double* g;
+    double r0;        // R_00 (real): PAM unit of the leaf stream
+    double thr;       // 64 varn^2
+    double best, lim; // incumbent distance and enqueue limit best + thr
+    int bestk;
+
+    // the M leaves below a node: t0 = residual on row 0, nb = partial distance of the node, code = node digits
+    __device__ __forceinline__ void leaf(cplx t0, double nb, int code) {
+        const double fI = E::fold(t0.x, r0), fQ = E::fold(t0.y, r0);
+        const double nodemin = fma(fI, fI, fma(fQ, fQ, nb));
+        if (nodemin <= lim) {  // rare at operating SNRs
+            if (nodemin <= best) {
+                double dI, dQ;
+                const int iI = E::slice(t0.x, g, dI), iQ = E::slice(t0.y, g, dQ);
+                const double val = nb + dI + dQ;
+                const int k = code + ((iQ * SQM + iI) << (E::BITS * (NTX - 1)));
+                if (val < best || (val == best && k < bestk)) {
+                    best = val;
+                    bestk = k;
+                    lim = HARD ? val : val + thr;
                 }
             }
+            if (!HARD) {
+                int* cntp = (int*)(ws + E::O_CNT);
+                const int slot = atomicAdd(cntp, 1);
+                if (slot < ENUM_QCAP) ((int*)(ws + E::O_Q))[slot] = code;
+            }
         }
     }
 
-    // fix stream S to constellation point m given residual rows acc[0..S]
-    template <int S_>
-    __device__ __forceinline__ void descend(const cplx (&acc)[NTX], double base, int kpart, int m, bool lane_varying) {
-        const double* gs = g + S_ * SQM;
-        const double eI = acc[S_].x - gs[m & (SQM - 1)];
-        const double eQ = acc[S_].y - gs[m >> (BITS / 2)];
-        const double nb = base + fma(eI, eI, eQ * eQ);
-        cplx nacc[NTX];
+    __device__ __forceinline__ void maybe_flush() {
+        if (!HARD) {
+            __syncwarp();
+            const int c = *(volatile int*)(ws + E::O_CNT);
+            if (c > ENUM_QCAP - 32 * SQM) {
+                double wb = best;
 #pragma unroll
-        for (int i = 0; i < S_; ++i) nacc[i] = csub(acc[i], tab[pair(i, S_) * M + m]);
-        const int nk = kpart + (m << (BITS * (NTX - 1 - S_)));
-        inner<S_ - 1>(nacc, nb, nk);
+                for (int o = 16; o > 0; o >>= 1) wb = fmin(wb, shfl_xor_d(wb, o));
+                enum_flush<NTX, SQM>(ws, wb);
+            }
+        }
     }
 
-    // enumerate streams S_ ... 1 with warp-uniform loops, then the leaves
+    // streams S_ ... 1 enumerated with warp-uniform loops
     template <int S_>
-    __device__ __forceinline__ void inner(const cplx (&acc)[NTX], double base, int kpart) {
+    __device__ __forceinline__ void inner(const cplx (&acc)[NTX], double base, int code, cplx r01) {
         if constexpr (S_ == 0) {
-            leaf(acc[0], base, kpart);
+            leaf(acc[0], base, code);
+        } else if constexpr (S_ == 1) {
+            // innermost node level: |u_1|^2 and R_01 x_1 are separable in the in-phase / quadrature indices
+            const double* g1 = g + SQM;
+            double dI1[SQM], dQ1[SQM];
+#pragma unroll
+            for (int a = 0; a < SQM; ++a) {
+                const double eI = acc[1].x - g1[a], eQ = acc[1].y - g1[a];
+                dI1[a] = eI * eI;
+                dQ1[a] = eQ * eQ;
+            }
+#pragma unroll 1
+            for (int iQ = 0; iQ < SQM; ++iQ) {
+                const double pQ = E::pam(iQ);
+                // t = acc0 - pQ * (i r01) = acc0 - pQ*(-r01.y + i r01.x)
+                const cplx tq = mk(fma(pQ, r01.y, acc[0].x), fma(-pQ, r01.x, acc[0].y));
+                const double bq = base + dQ1[iQ];
+                const int cq = code + ((iQ * SQM) << (E::BITS * (NTX - 2)));
+#pragma unroll
+                for (int iI = 0; iI < SQM; ++iI) {
+                    const double pI = E::pam(iI);
+                    const cplx t0 = mk(fma(-pI, r01.x, tq.x), fma(-pI, r01.y, tq.y));
+                    leaf(t0, bq + dI1[iI], cq + (iI << (E::BITS * (NTX - 2))));
+                }
+                maybe_flush();
+            }
         } else {
 #pragma unroll 1
-            for (int m = 0; m < M; ++m) descend<S_>(acc, base, kpart, m, false);
+            for (int m = 0; m < M; ++m) {
+                const double* gs = g + S_ * SQM;
+                const double eI = acc[S_].x - gs[m & (SQM - 1)];
+                const double eQ = acc[S_].y - gs[m >> E::HB];
+                const double nb = base + fma(eI, eI, eQ * eQ);
+                cplx nacc[NTX];
+#pragma unroll
+                for (int i = 0; i < NTX; ++i) nacc[i] = (i < S_) ? csub(acc[i], tab[E::pair(i, S_) * M + m]) : acc[i];
+                inner<S_ - 1>(nacc, nb, code + (m << (E::BITS * (NTX - 1 - S_))), r01);
+            }
         }
     }
 
-    // prefix streams NTX-1 ... NTX-PL fixed from the bits of p (lane-varying), then the uniform inner levels
+    // prefix streams (lane-varying digits taken from p), then the uniform inner levels
     template <int S_, int LEFT>
-    __device__ __forceinline__ void prefix(const cplx (&acc)[NTX], double base, int kpart, int p) {
+    __device__ __forceinline__ void prefix(const cplx (&acc)[NTX], double base, int code, int p, cplx r01) {
         if constexpr (LEFT == 0) {
-            inner<S_>(acc, base, kpart);
+            inner<S_>(acc, base, code, r01);
         } else {
-            const int m = (p >> (BITS * (LEFT - 1))) & (M - 1);
+            const int m = (p >> (E::BITS * (LEFT - 1))) & (M - 1);
             const double* gs = g + S_ * SQM;
             const double eI = acc[S_].x - gs[m & (SQM - 1)];
-            const double eQ = acc[S_].y - gs[m >> (BITS / 2)];
+            const double eQ = acc[S_].y - gs[m >> E::HB];
             const double nb = base + fma(eI, eI, eQ * eQ);
             cplx nacc[NTX];
 #pragma unroll
-            for (int i = 0; i < S_; ++i) nacc[i] = csub(acc[i], tab[pair(i, S_) * M + m]);
-            const int nk = kpart + (m << (BITS * (NTX - 1 - S_)));
-            prefix<S_ - 1, LEFT - 1>(nacc, nb, nk, p);
+            for (int i = 0; i < NTX; ++i) nacc[i] = (i < S_) ? csub(acc[i], tab[E::pair(i, S_) * M + m]) : acc[i];
+            prefix<S_ - 1, LEFT - 1>(nacc, nb, code + (m << (E::BITS * (NTX - 1 - S_))), p, r01);
         }
     }
 };
 
 template <int NTX, int SQM, bool HARD, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_enum(Dims d, const double* __restrict__ qr,
+__global__ void __launch_bounds__(WARPS * 32, 4) k_enum(Dims d, const double* __restrict__ qr,
                                                      const double* __restrict__ varn,
                                                      const int32_t* __restrict__ active, cplx* __restrict__ stat_m,
                                                      cplx* __restrict__ stat_R, int32_t* __restrict__ kstar,
                                                      double* __restrict__ lse_sym) {
-    typedef Enum<NTX, SQM, HARD> E;
+    typedef EnumT<NTX, SQM> E;
     constexpr int M = E::M;
-    __shared__ double smem[WARPS][E::TAB_DOUBLES];
+    __shared__ __align__(16) double smem[WARPS][E::WS_DOUBLES];
     const int b = blockIdx.y;
     if (active != nullptr && active[b] == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -348,10 +453,14 @@ __global__ void __launch_bounds__(WARPS * 32) k_enum(Dims d, const double* __res
     if (t >= d.T_d) return;
 
     const double* rec = qr + ((size_t)b * d.T_d + t) * d.rec;
-    // every lane keeps R and ytilde in registers (uniform loads)
-    cplx Rm[NTX][NTX];
+    double* ws = smem[warp];
+    cplx* tab = (cplx*)(ws + E::O_TAB);
+    double* g = ws + E::O_G;
     cplx yt[NTX];
+    cplx r01 = mk(0.0, 0.0);
+    double r00;
     {
+        cplx Rm[NTX][NTX];
         int o = 0;
 #pragma unroll
         for (int i = 0; i < NTX; ++i)
@@ -365,42 +474,47 @@ __global__ void __launch_bounds__(WARPS * 32) k_enum(Dims d, const double* __res
             yt[i] = mk(rec[o], rec[o + 1]);
             o += 2;
         }
+        r00 = Rm[0][0].x;
+        if (NTX > 1) r01 = Rm[0][NTX > 1 ? 1 : 0];
+        // tables: R_is * c_m for i<s, and the real PAM levels R_ss * pam_a
+#pragma unroll
+        for (int s = 1; s < NTX; ++s)
+#pragma unroll
+            for (int i = 0; i < s; ++i)
+                for (int m = lane; m < M; m += 32) tab[E::pair(i, s) * M + m] = cmul(Rm[i][s], E::cval(m));
+        if (lane < NTX * SQM) {
+            const int s = lane / SQM, a = lane % SQM;
+            double dd = 0.0;
+#pragma unroll
+            for (int q = 0; q < NTX; ++q)
+                if (q == s) dd = Rm[q][q].x;
+            g[lane] = dd * E::pam(a);
+        }
     }
     const double c0 = rec[NTX * (NTX + 1) + 2 * NTX];
-
-    double* my = smem[warp];
-    cplx* tab = (cplx*)my;
-    double* g = my + 2 * E::NPAIR1 * M;
-    // tables: R_is * c_m for i<s, and the real PAM levels R_ss * pam_a
+    const double vn = varn[b];
+    const double s2 = vn * vn, inv_s2 = 1.0 / s2;
+    if (lane == 0) {
 #pragma unroll
-    for (int s = 1; s < NTX; ++s)
-#pragma unroll
-        for (int i = 0; i < s; ++i)
-            for (int m = lane; m < M; m += 32) tab[E::pair(i, s) * M + m] = cmul(Rm[i][s], E::cval(m));
-    if (lane < NTX * SQM) {
-        const int s = lane / SQM, a = lane % SQM;
-        double dd = 0.0;
-#pragma unroll
-        for (int q = 0; q < NTX; ++q)
-            if (q == s) dd = Rm[q][q].x;
-        g[lane] = dd * E::pam(a);
+        for (int i = 0; i < NTX; ++i) {
+            ws[E::O_YT + 2 * i] = yt[i].x;
+            ws[E::O_YT + 2 * i + 1] = yt[i].y;
+        }
+        ws[E::O_C0] = c0;
+        ws[E::O_AREF] = 1e300;
+        ws[E::O_S2] = inv_s2;
+        *(int*)(ws + E::O_CNT) = 0;
     }
+    if (lane < E::NACC) ws[E::O_ACC + lane] = 0.0;
     __syncwarp();
 
-    E en;
-    en.tab = tab;
-    en.g = g;
-    const double vn = varn[b];
-    en.s2 = vn * vn;
-    en.inv_s2 = 1.0 / en.s2;
-    en.thr = SBCE_THR * en.s2;
-    en.S = 0.0;
-#pragma unroll
-    for (int j = 0; j < NTX; ++j) { en.mre[j] = 0; en.mim[j] = 0; en.Rd[j] = 0; }
-#pragma unroll
-    for (int q = 0; q < E::NPAIR1; ++q) en.Ro[q] = mk(0, 0);
-
-    // Babai point (successive slicing) gives a tight upper bound on min d2: start reference / incumbent
+    Scan<NTX, SQM, HARD> sc;
+    sc.ws = ws;
+    sc.tab = tab;
+    sc.g = g;
+    sc.r0 = r00;
+    sc.thr = SBCE_THR * s2;
+    // Babai point (successive slicing): a tight upper bound on min d2 -> incumbent
     {
         cplx acc[NTX];
 #pragma unroll
@@ -418,16 +532,21 @@ __global__ void __launch_bounds__(WARPS * 32) k_enum(Dims d, const double* __res
             for (int i = 0; i < NTX; ++i)
                 if (i < s) acc[i] = csub(acc[i], tab[E::pair(i, s) * M + m]);
         }
-        en.ref = base;
-        en.best = base;
-        en.bestk = k;
+        sc.best = base;
+        sc.bestk = k;
+        sc.lim = HARD ? base : base + sc.thr;
     }
 
-    for (int p = lane; p < E::NPREF; p += 32) en.template prefix<NTX - 1, E::PL>(yt, c0, 0, p);
+    // all lanes iterate the same number of prefixes (invalid ones carry an infinite partial distance)
+    for (int pb = 0; pb < E::NPREF; pb += 32) {
+        const int p = pb + lane;
+        const bool valid = p < E::NPREF;
+        sc.template prefix<NTX - 1, E::PL>(yt, valid ? c0 : 1e300, 0, valid ? p : 0, r01);
+    }
 
-    // ---- warp merge ---------------------------------------------------------
-    double best = en.best;
-    int bestk = en.bestk;
+    // ---- warp merge of the incumbent -------------------------------------------
+    double best = sc.best;
+    int bestk = sc.bestk;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double ob = shfl_xor_d(best, o);
@@ -437,7 +556,17 @@ __global__ void __launch_bounds__(WARPS * 32) k_enum(Dims d, const double* __res
     const size_t sidx = (size_t)b * d.T_d + t;
     if (kstar != nullptr && lane == 0) kstar[sidx] = bestk;
 
-    if (HARD) {
+    bool collapsed = HARD;
+    double S = 0.0;
+    if (!HARD) {
+        enum_flush<NTX, SQM>(ws, best);
+        S = ws[E::O_ACC];
+        // Nothing within 64 varn^2 of the incumbent was queued: only happens when |d2| is so large that
+        // its rounding error exceeds the window (e.g. a garbage start vector of norm 1e13); every weight
+        // but the best one underflows, so the posterior is the one-hot at k*.
+        if (!(S > 0.0) || !isfinite(S)) collapsed = true;
+    }
+    if (collapsed) {
         if (lane == 0) {
             cplx xs[NTX];
 #pragma unroll
@@ -448,36 +577,28 @@ __global__ void __launch_bounds__(WARPS * 32) k_enum(Dims d, const double* __res
 #pragma unroll
                 for (int j = 0; j < NTX; ++j) stat_R[(sidx * NTX + i) * NTX + j] = cmulc(xs[j], xs[i]);
             }
-            if (lse_sym != nullptr) lse_sym[sidx] = -best * en.inv_s2;
+            if (lse_sym != nullptr) lse_sym[sidx] = -best * inv_s2;
         }
         return;
     }
-
-    double refg = en.ref;
+    if (lane == 0) {
+        const double invS = 1.0 / S;
+        const double* A = ws + E::O_ACC;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) refg = fmin(refg, shfl_xor_d(refg, o));
-    if (en.S > 0.0) en.rescale(exp((refg - en.ref) * en.inv_s2));
-    const double S = warp_sum(en.S);
-    const double invS = 1.0 / S;
-#pragma unroll
-    for (int j = 0; j < NTX; ++j) {
-        const double a = warp_sum(en.mre[j]), c = warp_sum(en.mim[j]), r = warp_sum(en.Rd[j]);
-        if (lane == 0) {
-            stat_m[sidx * NTX + j] = mk(a * invS, c * invS);
-            stat_R[(sidx * NTX + j) * NTX + j] = mk(r * invS, 0.0);
+        for (int j = 0; j < NTX; ++j) {
+            stat_m[sidx * NTX + j] = mk(A[1 + j] * invS, A[1 + NTX + j] * invS);
+            stat_R[(sidx * NTX + j) * NTX + j] = mk(A[1 + 2 * NTX + j] * invS, 0.0);
         }
-    }
 #pragma unroll
-    for (int s = 1; s < NTX; ++s)
+        for (int s = 1; s < NTX; ++s)
 #pragma unroll
-        for (int i = 0; i < s; ++i) {
-            const double a = warp_sum(en.Ro[E::pair(i, s)].x), c = warp_sum(en.Ro[E::pair(i, s)].y);
-            if (lane == 0) {
-                stat_R[(sidx * NTX + i) * NTX + s] = mk(a * invS, c * invS);
-                stat_R[(sidx * NTX + s) * NTX + i] = mk(a * invS, -c * invS);
+            for (int i = 0; i < s; ++i) {
+                const double a = A[1 + 3 * NTX + 2 * E::pair(i, s)] * invS, c = A[1 + 3 * NTX + 2 * E::pair(i, s) + 1] * invS;
+                stat_R[(sidx * NTX + i) * NTX + s] = mk(a, c);
+                stat_R[(sidx * NTX + s) * NTX + i] = mk(a, -c);
             }
-        }
-    if (lse_sym != nullptr && lane == 0) lse_sym[sidx] = -refg * en.inv_s2 + log(S);
+        if (lse_sym != nullptr) lse_sym[sidx] = -ws[E::O_AREF] * inv_s2 + log(S);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -532,29 +653,25 @@ static cudaError_t run_enum_ntx(const Dims& d, int nb, const double* qr, const d
     }
 }
 
-cudaError_t launch_estep(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
-                         const double* varn, const int32_t* active, double* qr, double* stat_m, double* stat_R,
-                         int32_t* kstar, double* lse_sym, cudaStream_t s) {
-    cudaError_t e;
+cudaError_t launch_heff_qr(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
+                           const int32_t* active, double* qr, cudaStream_t s) {
     switch (d.n_tx) {
-        case 1:
-            e = run_heff_ntx<1>(d, nb, Yd, PsiD, theta, active, qr, s);
-            if (e != cudaSuccess) return e;
-            return run_enum_ntx<1>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
-        case 2:
-            e = run_heff_ntx<2>(d, nb, Yd, PsiD, theta, active, qr, s);
-            if (e != cudaSuccess) return e;
-            return run_enum_ntx<2>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
-        case 3:
-            e = run_heff_ntx<3>(d, nb, Yd, PsiD, theta, active, qr, s);
-            if (e != cudaSuccess) return e;
-            return run_enum_ntx<3>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
-        case 4:
-            e = run_heff_ntx<4>(d, nb, Yd, PsiD, theta, active, qr, s);
-            if (e != cudaSuccess) return e;
-            return run_enum_ntx<4>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
-        default:
-            return cudaErrorInvalidValue;
+        case 1: return run_heff_ntx<1>(d, nb, Yd, PsiD, theta, active, qr, s);
+        case 2: return run_heff_ntx<2>(d, nb, Yd, PsiD, theta, active, qr, s);
+        case 3: return run_heff_ntx<3>(d, nb, Yd, PsiD, theta, active, qr, s);
+        case 4: return run_heff_ntx<4>(d, nb, Yd, PsiD, theta, active, qr, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_enum(const Dims& d, int nb, const double* qr, const double* varn, const int32_t* active,
+                        double* stat_m, double* stat_R, int32_t* kstar, double* lse_sym, cudaStream_t s) {
+    switch (d.n_tx) {
+        case 1: return run_enum_ntx<1>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
+        case 2: return run_enum_ntx<2>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
+        case 3: return run_enum_ntx<3>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
+        case 4: return run_enum_ntx<4>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
+        default: return cudaErrorInvalidValue;
     }
 }
 

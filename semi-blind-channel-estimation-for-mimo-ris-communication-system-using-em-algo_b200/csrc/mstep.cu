@@ -148,9 +148,8 @@ __global__ void k_pad(Dims d, cplx* __restrict__ Gout, const int32_t* __restrict
 }
 
 template <int NTX>
-static cudaError_t run_gram(const Dims& d, int nb, const double* Psi, int T, const double* Y, const double* sm,
-                            const double* sR, const double* Ginit, double* Gout, const int32_t* active,
-                            cudaStream_t s) {
+static cudaError_t run_gram(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Ginit,
+                            double* Gout, const int32_t* active, cudaStream_t s) {
     const int P = d.N1 * (d.N1 + 1) / 2;
     dim3 grid((P + GR_THREADS - 1) / GR_THREADS, nb);
     size_t smem = sizeof(cplx) * (size_t)(GR_TC * d.N1 + GR_TC * NTX * NTX);
@@ -164,17 +163,20 @@ static cudaError_t run_gram(const Dims& d, int nb, const double* Psi, int T, con
     return cudaGetLastError();
 }
 
-cudaError_t launch_gram(const Dims& d, int nb, const double* Psi, int T, const double* Y, const double* sm,
-                        const double* sR, const double* Ginit, double* Gout, const int32_t* active, cudaStream_t s) {
-    cudaError_t e;
+cudaError_t launch_gram(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Ginit,
+                        double* Gout, const int32_t* active, cudaStream_t s) {
     switch (d.n_tx) {
-        case 1: e = run_gram<1>(d, nb, Psi, T, Y, sm, sR, Ginit, Gout, active, s); break;
-        case 2: e = run_gram<2>(d, nb, Psi, T, Y, sm, sR, Ginit, Gout, active, s); break;
-        case 3: e = run_gram<3>(d, nb, Psi, T, Y, sm, sR, Ginit, Gout, active, s); break;
-        case 4: e = run_gram<4>(d, nb, Psi, T, Y, sm, sR, Ginit, Gout, active, s); break;
+        case 1: return run_gram<1>(d, nb, Psi, T, sR, Ginit, Gout, active, s);
+        case 2: return run_gram<2>(d, nb, Psi, T, sR, Ginit, Gout, active, s);
+        case 3: return run_gram<3>(d, nb, Psi, T, sR, Ginit, Gout, active, s);
+        case 4: return run_gram<4>(d, nb, Psi, T, sR, Ginit, Gout, active, s);
         default: return cudaErrorInvalidValue;
     }
-    if (e != cudaSuccess) return e;
+}
+
+cudaError_t launch_rhs_pad(const Dims& d, int nb, const double* Psi, int T, const double* Y, const double* sm,
+                           const double* Ginit, double* Gout, const int32_t* active, cudaStream_t s) {
+    cudaError_t e;
     {
         const int total = d.N1 * d.n_tx * d.n_rx;
         dim3 grid((total + 127) / 128, nb);

@@ -90,9 +90,37 @@ def _np_c128(a, shape, name):
     return a
 
 
+def alloc_host_outputs(prob: Problem, B, want=("kstar", "lse", "nmse", "iters", "status"), pinned=False) -> Result:
+    """Output arrays for run_host(out=...); pinned=True allocates page-locked memory through torch."""
+    def mk(shape, dtype):
+        if pinned:
+            import torch
+
+            tdt = {np.complex128: torch.complex128, np.float64: torch.float64, np.int32: torch.int32}[dtype]
+            return torch.empty(shape, dtype=tdt).pin_memory().numpy()
+        return np.empty(shape, dtype=dtype)
+
+    out = Result(theta=mk((B, prob.L, prob.n_rx), np.complex128))
+    if "kstar" in want:
+        out.kstar = mk((B, prob.T_d), np.int32)
+    if "llf" in want:
+        out.llf = mk((B, prob.itera), np.float64)
+    if "lse" in want:
+        out.lse = mk((B, prob.itera), np.float64)
+    if "nmse" in want:
+        out.nmse = mk((B,), np.float64)
+    if "iters" in want:
+        out.iters = mk((B,), np.int32)
+    if "status" in want:
+        out.status = mk((B,), np.int32)
+    return out
+
+
 def run_host(prob: Problem, Yd, Yp, PsiD, PsiP, Xp, varn, theta0=None, h_true=None, Xd_true=None,
-             want=("kstar", "llf", "lse", "nmse", "iters", "status"), device=0) -> Result:
+             want=("kstar", "llf", "lse", "nmse", "iters", "status"), device=0, out: Optional[Result] = None) -> Result:
     """numpy route (host buffers; copies are inside the call)."""
+    if out is not None:
+        return _run_host_into(prob, Yd, Yp, PsiD, PsiP, Xp, varn, theta0, h_true, Xd_true, device, out)
     lib = _lib.require_device()
     B = int(np.asarray(Yd).shape[0])
     sh = prob.shapes(B)
@@ -130,6 +158,33 @@ def run_host(prob: Problem, Yd, Yp, PsiD, PsiP, Xp, varn, theta0=None, h_true=No
     if "status" in want:
         out.status = np.empty((B,), dtype=np.int32)
         io.status = out.status.ctypes.data
+    cfg = prob.cfg(B)
+    _lib.check(lib.sbce_em_batch_host(C.byref(cfg), C.byref(io), device))
+    return out
+
+
+def _run_host_into(prob, Yd, Yp, PsiD, PsiP, Xp, varn, theta0, h_true, Xd_true, device, out: Result) -> Result:
+    """run_host with caller-owned (e.g. pinned) input and output arrays: no allocation, no conversion."""
+    lib = _lib.require_device()
+    B = int(Yd.shape[0])
+    sh = prob.shapes(B)
+    ins = dict(Yd=Yd, Yp=Yp, PsiD=PsiD, PsiP=PsiP, Xp=Xp, theta0=theta0, h_true=h_true, Xd_true=Xd_true)
+    io = _lib.Io()
+    for k in _IN_C:
+        v = ins[k]
+        if v is None:
+            continue
+        if v.dtype != np.complex128 or not v.flags.c_contiguous or v.shape != tuple(sh[k]):
+            raise ValueError("%s must be C-contiguous complex128 of shape %s" % (k, sh[k]))
+        setattr(io, k, v.ctypes.data)
+    if varn.dtype != np.float64 or varn.shape != (B,):
+        raise ValueError("varn must be float64 of shape (B,)")
+    io.varn = varn.ctypes.data
+    io.theta = out.theta.ctypes.data
+    for k in ("kstar", "llf", "lse", "nmse", "iters", "status"):
+        a = getattr(out, k)
+        if a is not None and not (k == "llf" and Xd_true is None) and not (k == "nmse" and h_true is None):
+            setattr(io, k, a.ctypes.data)
     cfg = prob.cfg(B)
     _lib.check(lib.sbce_em_batch_host(C.byref(cfg), C.byref(io), device))
     return out
@@ -264,3 +319,16 @@ def fp64_peak_tflops():
 
 def launch_count(reset=False):
     return int(_lib.load().sbce_launch_count(1 if reset else 0))
+
+
+def profile_begin():
+    _lib.check(_lib.load().sbce_profile_begin())
+
+
+def profile_end():
+    """-> {phase: (milliseconds, timed launches)} summed since profile_begin()."""
+    n = len(_lib.PHASES)
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    _lib.check(_lib.load().sbce_profile_end(ms, cnt, n))
+    return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.PHASES)}

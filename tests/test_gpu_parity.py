@@ -205,8 +205,9 @@ def test_multi_detector_golden(S, orc, name):
 
 
 BATCH_CASES = [
-    # N, n_tx, n_rx, M, T_p, T_d, itera, varn, mode
-    (32, 2, 2, 4, 40, 50, 10, 0.1, "soft"),      # shipped config 1, well-posed point
+    # N, n_tx, n_rx, M, T_p, T_d, itera, varn, mode   (T_p <= N keeps the "pm" pilot design's LS start
+    # well-posed: its DFT rows repeat with period N, see test_garbage_start_stays_finite)
+    (32, 2, 2, 4, 32, 58, 10, 0.1, "soft"),      # shipped config 1 shape (N=32, 2x2, QPSK, 10 iterations)
     (32, 1, 8, 4, 16, 60, 6, 0.1, "soft"),       # shipped config 2 shape
     (16, 2, 2, 16, 20, 60, 4, 0.4, "soft"),
     (16, 2, 2, 16, 20, 60, 4, 0.4, "hard"),
@@ -238,6 +239,34 @@ def test_em_batch_matches_oracle(S, orc, case):
             np.testing.assert_allclose(res.lse[b], np.array(tr["lse"]), rtol=1e-9)
 
 
+def test_garbage_start_stays_finite(S, orc):
+    """N=32, T_p=40 with the Proposed-method pilot design: pinv() of the rank-deficient pilot matrix
+    inverts singular values of 3e-14 and the reference's own LS start has norm ~1e13.  The first E-step
+    then sees |d2| ~ 1e27 whose rounding error dwarfs varn^2; the posterior must collapse to the
+    arg-min hypothesis (as float(beta) underflow does in the reference) instead of producing NaN."""
+    N, n_tx, n_rx, M, T_p, T_d, itera, varn = 32, 2, 2, 4, 40, 50, 4, 0.1
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn, 4, seed=42, legacy=False)
+    assert np.linalg.norm(tb.theta0[0]) > 1e9
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera)
+    res = S.run_host(prob, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, tb.varn, theta0=tb.theta0, h_true=tb.h)
+    assert np.isfinite(res.theta).all() and (res.status == 0).all()
+    assert res.nmse.max() < 50.0
+
+
+def test_zero_start_config1_as_shipped(S, orc):
+    """Proposed_method_NMSEvsTp.py as shipped: N=32, 2x2, QPSK, T_d=50, zero start, 10 iterations,
+    pilot design exp(-j2pi t n/T_p) + ones row, at its well-posed sweep point T_p=40."""
+    N, n_tx, n_rx, M, T_p, T_d, itera, varn = 32, 2, 2, 4, 40, 50, 10, 0.1
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn, 3, seed=3, legacy=True, variant="top_tp")
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera, zero_start=True)
+    res = S.run_host(prob, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, tb.varn, h_true=tb.h)
+    for b in range(3):
+        ref = orc.em(tb.Yd[b], tb.Yp[b], tb.PsiD[b], tb.PsiP[b], tb.Xp[b], M, varn, itera, theta0=None)
+        assert relerr(res.theta[b], ref) < RTOL
+        nm = orc.nmse(ref, tb.h[b])
+        assert abs(res.nmse[b] - nm) <= 5e-5 * nm
+
+
 def test_zero_start_and_shared_status(S, orc):
     """theta0 = 0 start of the top-level scripts (Proposed_method_NMSEvsTp.py:45)."""
     N, n_tx, n_rx, M, T_p, T_d, itera, varn = 16, 2, 2, 4, 24, 40, 6, 0.1
@@ -246,6 +275,63 @@ def test_zero_start_and_shared_status(S, orc):
     res = S.run_host(prob, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, tb.varn, h_true=tb.h)
     for b in range(3):
         ref = orc.em(tb.Yd[b], tb.Yp[b], tb.PsiD[b], tb.PsiP[b], tb.Xp[b], M, varn, itera, theta0=None)
+        assert relerr(res.theta[b], ref) < RTOL
+
+
+@pytest.mark.parametrize("name", golden_names(["pm", "pm_beta"]))
+def test_em_pm_golden(S, orc, name):
+    """Partitioned EM against the literal PM.py / PM_beta.py (genie stop active, quirks on)."""
+    meta, g = load_golden(name)
+    n_tx, n_rx, M = int(meta["n_tx"]), int(meta["n_rx"]), int(meta["M"])
+    T_d, T_p, varn, itera = int(meta["T_d"]), int(meta["T_p"]), float(meta["varn"]), int(meta["itera"])
+    Y_d, Y_p, Z_p, PsiTilde_td = _ref_objects(g, n_rx)
+    cons = orc.qam_constellation(M)
+    h0 = g["theta0"].reshape(-1, 1)
+    pr = int(meta["partition_r"])
+    if str(meta["kind"]) == "pm":
+        table = orc.hypothesis_table(cons, n_tx)
+        th = S.em_pm(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, table, M, varn, itera, h0, g["h"].reshape(-1), n_tx, pr,
+                     None, cons)
+    else:
+        th = S.em_pm_beta(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, M, varn, itera, h0, g["h"].reshape(-1), n_tx, pr,
+                          None, cons)
+    assert relerr(th.reshape(g["theta_ref"].shape), g["theta_ref"]) < RTOL
+
+
+PM_CASES = [
+    # N, n_tx, n_rx, M, T_p, T_d, itera, varn, mode, partition_r, quirks
+    (8, 2, 2, 4, 8, 30, 3, 0.2, "pm", 0, True), (8, 2, 2, 4, 8, 30, 3, 0.2, "pm_beta", 0, True),
+    (8, 3, 3, 4, 8, 40, 3, 0.3, "pm_beta", 2, True), (8, 3, 4, 16, 8, 40, 2, 0.5, "pm_beta", 4, False),
+    (6, 4, 4, 4, 6, 48, 2, 0.3, "pm", 2, True), (6, 4, 4, 16, 6, 48, 2, 0.6, "pm_beta", 4, False),
+    (6, 2, 4, 16, 6, 30, 2, 0.6, "pm_beta", 4, True),   # p+1 = n_tx: no zero-forced streams
+]
+
+
+@pytest.mark.parametrize("case", PM_CASES)
+def test_em_pm_batch_matches_oracle(S, orc, case):
+    N, n_tx, n_rx, M, T_p, T_d, itera, varn, mode, pr, quirks = case
+    B = 3
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn, B, seed=77, legacy=False)
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera, mode=mode, partition_r=pr,
+                     quirks=quirks, genie_stop=False)
+    res = S.run_host(prob, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, tb.varn, theta0=tb.theta0, h_true=tb.h)
+    for b in range(B):
+        ref = orc.em_pm(tb.Yd[b], tb.Yp[b], tb.PsiD[b], tb.PsiP[b], tb.Xp[b], M, varn, itera, tb.theta0[b],
+                        h_true=tb.h[b], partition_r=pr, weighted=(mode == "pm_beta"), genie_stop=False,
+                        quirks=quirks, how="solve")
+        assert relerr(res.theta[b], ref) < 1e-8, (b, relerr(res.theta[b], ref))
+
+
+def test_genie_stop_iteration_counts(S, orc):
+    N, n_tx, n_rx, M, T_p, T_d, itera, varn = 8, 2, 2, 4, 8, 40, 6, 0.1
+    B = 6
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn, B, seed=5, legacy=False)
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera, genie_stop=True)
+    res = S.run_host(prob, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, tb.varn, theta0=tb.theta0, h_true=tb.h)
+    for b in range(B):
+        ref, tr = orc.em(tb.Yd[b], tb.Yp[b], tb.PsiD[b], tb.PsiP[b], tb.Xp[b], M, varn, itera, theta0=tb.theta0[b],
+                         h_true=tb.h[b], genie_stop=True, return_trace=True)
+        assert int(res.iters[b]) == tr["iters"]
         assert relerr(res.theta[b], ref) < RTOL
 
 

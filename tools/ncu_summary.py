@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Summarise ncu outputs brought back in gpurun_out/ into tracked files under profiles/.
+  launches: python tools/ncu_summary.py launches gpurun_out/launches.csv profiles/r01_launches.md "<command>"
+  full:     python tools/ncu_summary.py full gpurun_out/prof_enum.ncu-rep profiles/r01_enum_full.csv
+"""
+import collections, csv, re, subprocess, sys
+
+KEEP = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
+        "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+
+
+def launches(src, dst, cmd):
+    lines = [l for l in open(src) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = re.sub(r"\(.*", "", row["Kernel Name"])
+        v = float(row["Metric Value"].replace(",", ""))
+        v *= {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(row["Metric Unit"], 1.0)
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    with open(dst, "w") as f:
+        f.write("# ncu launch list (gpu__time_duration.sum, --clock-control none)\n\n")
+        f.write("command: `%s`\n\n" % cmd)
+        f.write("Per-launch times are cold-cache and serialised; compare SHARES with bench.py's CUDA-event phase timers.\n\n")
+        f.write("| kernel | launches | total ms | share | avg us |\n|---|---:|---:|---:|---:|\n")
+        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("| `%s` | %d | %.3f | %.1f%% | %.1f |\n" % (k, n, t / 1e6, 100 * t / tot, t / n / 1e3))
+    print(open(dst).read())
+
+
+def full(src, dst):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(dst, "w") as f:
+        w = csv.writer(f)
+        w.writerow(["metric", "unit"] + ["launch%d" % i for i in range(len(rows) - 2)])
+        w.writerow(["Kernel Name", ""] + [r[hdr.index("Kernel Name")][:60] for r in rows[2:]])
+        for m in KEEP:
+            if m in hdr:
+                i = hdr.index(m)
+                w.writerow([m, units[i]] + [r[i] for r in rows[2:]])
+    print(open(dst).read())
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+    else:
+        full(sys.argv[2], sys.argv[3])
