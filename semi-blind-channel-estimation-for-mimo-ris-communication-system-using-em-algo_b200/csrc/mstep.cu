@@ -200,43 +200,97 @@ cudaError_t launch_rhs_pad(const Dims& d, int nb, const double* Psi, int T, cons
 // Blocked Cholesky of the augmented trapezoid + back substitution
 // ---------------------------------------------------------------------------
 constexpr int CH_THREADS = 256;
-constexpr int CH_NB = 16;
+constexpr int CH_WARPS = CH_THREADS / 32;
+constexpr int CH_NB = 16;            // panel width
+constexpr int CH_SP = CH_NB + 1;     // row stride (complex) of the shared panel: odd -> conflict-free column walks
 
-// shared-memory panel layout: element (local row lr, panel column q) lives at
-//   Ps[(q*4 + (lr&3)) * nbr + (lr>>2)]      nbr = block rows of the panel (padded odd)
-// so that the 4 rows of a micro-tile sit in 4 planes and consecutive micro-tile
-// indices are consecutive 16-byte words (conflict-free, broadcast-friendly).
-__device__ __forceinline__ int ps_index(int lr, int q, int nbr) { return (q * 4 + (lr & 3)) * nbr + (lr >> 2); }
+__device__ __forceinline__ void dmma16x8x8(double (&c)[4], const double (&a)[4], double b0, double b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b0), "d"(b1));
+}
 
-__global__ void __launch_bounds__(CH_THREADS) k_chol(Dims d, cplx* __restrict__ Gall, cplx* __restrict__ theta,
-                                                     const int32_t* __restrict__ active, int32_t* __restrict__ stat) {
+// LEFT-looking blocked complex Cholesky on the FP64 tensor path (mma.sync m16n8k8.f64, "DMMA"):
+// panel k (16 columns, all rows below its diagonal block) is brought up to date with ALL previous
+// panels in one register-accumulated product
+//   S[r][c] = A[r][c] - sum_{q<k0} C[r][q] conj(C[k0+c][q])
+// Each warp owns 16-row tiles of the panel; the operand fragments are loaded straight from the
+// factor in global memory (L2 / L1 resident, 16-byte complex loads in fragment order, no shared
+// staging), 8 DMMAs per 8 previous columns.  The updated panel goes to shared memory, its diagonal
+// block is factored by one warp, the rows below are solved by forward substitution (thread per
+// row) and the panel is written once; the trailing matrix is never rewritten.
+__global__ void __launch_bounds__(CH_THREADS, 2) k_chol(Dims d, cplx* __restrict__ Gall, cplx* __restrict__ theta,
+                                                        const int32_t* __restrict__ active, int32_t* __restrict__ stat) {
     extern __shared__ double2 csm[];
     const int b = blockIdx.x;
     if (active != nullptr && active[b] == 0) return;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
     const int Lp = d.Lp, Ltot = d.Ltot, ld = d.Lp;
     cplx* A = Gall + (size_t)b * Ltot * Lp;
 
-    const int nbr_max = (Ltot / 4) | 1;
-    cplx* sD = csm;                        // [CH_NB][CH_NB+1] diagonal block / its factor
-    cplx* sW = sD + CH_NB * (CH_NB + 1);   // [CH_NB][CH_NB+1] inverse of the factor
-    cplx* Ps = sW + CH_NB * (CH_NB + 1);   // panel, CH_NB*4*nbr_max
+    cplx* sD = csm;                            // [CH_NB][CH_NB+1] diagonal block / its factor (also reduction scratch)
+    cplx* buf = sD + 2 * CH_NB * (CH_NB + 1);  // updated panel [rows][CH_SP]; later theta
     __shared__ int s_bad;
     if (tid == 0) s_bad = 0;
 
     for (int k0 = 0; k0 < Lp; k0 += CH_NB) {
-        const int nb = min(CH_NB, Lp - k0);
-        const int c1 = k0 + nb;  // first trailing row/col
-        __syncthreads();
-        // ---- diagonal block -> shared
-        for (int e = tid; e < nb * nb; e += CH_THREADS) {
-            const int r = e / nb, c = e % nb;
-            sD[r * (CH_NB + 1) + c] = (c <= r) ? A[(size_t)(k0 + r) * ld + k0 + c] : mk(0.0, 0.0);
+        const int nb = min(CH_NB, Lp - k0);   // multiple of 4
+        const int rows = Ltot - k0;           // rows of the panel including its diagonal block
+        const int nrt = (rows + 15) >> 4;
+        __syncthreads();                      // previous panel fully written (global) and buf free
+        for (int rt = warp; rt < nrt; rt += CH_WARPS) {
+            const int r0 = rt << 4;
+            // accumulators: [n-tile][c0..c3], real and imaginary parts
+            double cr[2][4], ci[2][4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { cr[j][e] = 0.0; ci[j][e] = 0.0; }
+            const int ra = min(r0 + g, rows - 1), rb8 = min(r0 + g + 8, rows - 1);
+            const cplx* pa0 = A + (size_t)(k0 + ra) * ld + tig;
+            const cplx* pa1 = A + (size_t)(k0 + rb8) * ld + tig;
+            const cplx* pb0 = A + (size_t)min(k0 + g, Ltot - 1) * ld + tig;
+            const cplx* pb1 = A + (size_t)min(k0 + 8 + g, Ltot - 1) * ld + tig;
+#pragma unroll 2
+            for (int q0 = 0; q0 < k0; q0 += 8) {
+                const cplx a0 = pa0[q0], a1 = pa1[q0], a2 = pa0[q0 + 4], a3 = pa1[q0 + 4];
+                const cplx b00 = pb0[q0], b01 = pb0[q0 + 4], b10 = pb1[q0], b11 = pb1[q0 + 4];
+                const double ar[4] = {a0.x, a1.x, a2.x, a3.x};
+                const double ai[4] = {a0.y, a1.y, a2.y, a3.y};
+                // sum_q a conj(b):  re += ar br + ai bi ;  im += ai br - ar bi
+                dmma16x8x8(cr[0], ar, b00.x, b01.x);
+                dmma16x8x8(cr[0], ai, b00.y, b01.y);
+                dmma16x8x8(ci[0], ai, b00.x, b01.x);
+                dmma16x8x8(ci[0], ar, -b00.y, -b01.y);
+                dmma16x8x8(cr[1], ar, b10.x, b11.x);
+                dmma16x8x8(cr[1], ai, b10.y, b11.y);
+                dmma16x8x8(ci[1], ai, b10.x, b11.x);
+                dmma16x8x8(ci[1], ar, -b10.y, -b11.y);
+            }
+            // S = A - acc  -> shared panel (fragment: rows g / g+8, columns 8j + 2 tig + {0,1})
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int lr = r0 + g + 8 * h;
+                    const int c = 8 * j + 2 * tig;
+                    if (lr < rows && c < nb) {
+                        const cplx* src = A + (size_t)(k0 + lr) * ld + k0 + c;
+                        const cplx v0 = src[0], v1 = src[1];
+                        buf[lr * CH_SP + c] = mk(v0.x - cr[j][2 * h], v0.y - ci[j][2 * h]);
+                        buf[lr * CH_SP + c + 1] = mk(v1.x - cr[j][2 * h + 1], v1.y - ci[j][2 * h + 1]);
+                    }
+                }
         }
         __syncthreads();
-        // ---- unblocked Cholesky of the nb x nb block by warp 0 (lane = row), then its inverse
+        // ---- diagonal block (local rows 0..nb) -> sD, unblocked Cholesky by warp 0 (lane = row)
         if (tid < 32) {
             const int r = tid;
+            if (r < nb)
+                for (int c = 0; c < nb; ++c) sD[r * (CH_NB + 1) + c] = (c <= r) ? buf[r * CH_SP + c] : mk(0.0, 0.0);
+            __syncwarp();
             for (int c = 0; c < nb; ++c) {
                 double piv = sD[c * (CH_NB + 1) + c].x;
                 if (!(piv > 0.0)) {
@@ -255,92 +309,27 @@ __global__ void __launch_bounds__(CH_THREADS) k_chol(Dims d, cplx* __restrict__ 
                 }
                 __syncwarp();
             }
-            // W = inverse of lower-triangular factor: lane = column of W
-            if (r < nb) {
-                const int c = r;
-                for (int i = 0; i < nb; ++i) {
-                    cplx v = mk(0.0, 0.0);
-                    if (i == c) v = mk(1.0 / sD[i * (CH_NB + 1) + i].x, 0.0);
-                    else if (i > c) {
-                        cplx acc = mk(0.0, 0.0);
-                        for (int q = c; q < i; ++q) cfma(acc, sD[i * (CH_NB + 1) + q], sW[q * (CH_NB + 1) + c]);
-                        const double invd = 1.0 / sD[i * (CH_NB + 1) + i].x;
-                        v = mk(-acc.x * invd, -acc.y * invd);
-                    }
-                    sW[i * (CH_NB + 1) + c] = v;
-                }
-            }
         }
         __syncthreads();
-        // ---- write the factored diagonal block back
+        // ---- write the factored diagonal block; rows below: forward substitution X D^H = S (thread per row)
         for (int e = tid; e < nb * nb; e += CH_THREADS) {
             const int r = e / nb, c = e % nb;
             if (c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = sD[r * (CH_NB + 1) + c];
         }
-        // ---- panel rows: X = A21 * W^H   (thread per row), to global and to the shared panel
-        const int nrows = Ltot - c1;
-        const int nbr = (nrows / 4) | 1;
-        for (int lr = tid; lr < nrows; lr += CH_THREADS) {
-            cplx* rowp = A + (size_t)(c1 + lr) * ld + k0;
-            cplx a[CH_NB];
-#pragma unroll
-            for (int q = 0; q < CH_NB; ++q) a[q] = (q < nb) ? rowp[q] : mk(0.0, 0.0);
-#pragma unroll
-            for (int c = 0; c < CH_NB; ++c) {
-                if (c < nb) {
-                    cplx x = mk(0.0, 0.0);
-#pragma unroll
-                    for (int q = 0; q < CH_NB; ++q)
-                        if (q <= c) cfmac(x, a[q], sW[c * (CH_NB + 1) + q]);  // a_q * conj(W[c][q])
-                    rowp[c] = x;
-                    Ps[ps_index(lr, c, nbr)] = x;
-                }
+        for (int lr = nb + tid; lr < rows; lr += CH_THREADS) {
+            cplx* xr = buf + lr * CH_SP;  // the row is solved in place in shared memory
+            cplx* dst = A + (size_t)(k0 + lr) * ld + k0;
+            for (int c = 0; c < nb; ++c) {
+                cplx v = xr[c];
+                const cplx* dc = sD + c * (CH_NB + 1);
+                for (int q = 0; q < c; ++q) cfmsc(v, xr[q], dc[q]);  // v -= x_q conj(D[c][q])
+                v = cscale(v, 1.0 / dc[c].x);
+                xr[c] = v;
+                dst[c] = v;
             }
-        }
-        __syncthreads();
-        // ---- trailing update with 4x4 micro-tiles: A[r][c] -= sum_q X[r][q] conj(X[c][q]),  c in [c1, Lp)
-        const int nr = nrows / 4;         // block rows (Ltot, Lp, c1 are multiples of 4)
-        const int nc = (Lp - c1) / 4;     // block cols
-        const int ntri = nc * (nc + 1) / 2;
-        const int nblk = ntri + (nr - nc) * nc;
-        for (int p = tid; p < nblk; p += CH_THREADS) {
-            int br, bc;
-            if (p < ntri) {
-                br = (int)((sqrtf(8.0f * p + 1.0f) - 1.0f) * 0.5f);
-                while ((br + 1) * (br + 2) / 2 <= p) ++br;
-                while (br * (br + 1) / 2 > p) --br;
-                bc = p - br * (br + 1) / 2;
-            } else {
-                const int q = p - ntri;
-                br = nc + q / nc;
-                bc = q % nc;
-            }
-            cplx acc[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = mk(0.0, 0.0);
-            for (int q = 0; q < nb; ++q) {
-                cplx xa[4], xb[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) xa[i] = Ps[(q * 4 + i) * nbr + br];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) xb[j] = Ps[(q * 4 + j) * nbr + bc];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) cfmac(acc[i][j], xa[i], xb[j]);
-            }
-            cplx* base = A + (size_t)(c1 + 4 * br) * ld + (c1 + 4 * bc);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    cplx v = base[(size_t)i * ld + j];
-                    base[(size_t)i * ld + j] = csub(v, acc[i][j]);
-                }
         }
     }
+    cplx* Ps = buf;
     __syncthreads();
     if (tid == 0 && s_bad && stat) atomicOr(&stat[b], SBCE_ST_NOT_PD);
 
@@ -401,8 +390,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chol(Dims d, cplx* __restrict__ 
 
 cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
                               cudaStream_t s) {
-    const int nbr_max = (d.Ltot / 4) | 1;
-    size_t panel = (size_t)CH_NB * 4 * nbr_max;
+    size_t panel = (size_t)d.Ltot * CH_SP;
     size_t thsz = (size_t)d.Lp * d.n_rx;
     size_t smem = sizeof(cplx) * (2 * CH_NB * (CH_NB + 1) + (panel > thsz ? panel : thsz));
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
