@@ -56,6 +56,10 @@ extern "C" {
                                    candidate vector (PM.py:102); cleared = corrected behaviour             */
 #define SBCE_FLAG_PSI_SHARED 4u /* PsiP / PsiD are shared by all trials of the batch ([T][N+1], no batch dim) */
 #define SBCE_FLAG_ZERO_START 8u /* theta0 is ignored, EM starts from 0 (Proposed_method_NMSEvsTp.py:45)      */
+#define SBCE_FLAG_FULL_SCAN 16u /* E-step visits every node of the hypothesis tree.  Default (flag clear): subtrees
+                                   whose partial distance already exceeds the incumbent + 64 varn^2 are skipped --
+                                   they could neither improve the arg-min nor enter the posterior sums, so the
+                                   outputs are BIT-IDENTICAL to the full scan (tests/test_gpu_parity.py)              */
 
 /* per-trial status bits */
 #define SBCE_ST_NOT_PD 1    /* non-positive pivot in the Cholesky of the normal matrix (singular M-step) */

@@ -124,8 +124,7 @@ static int em_chunk(const Dims& d, int nb, const sbce_io& io, Workspace& ws, cud
         // pilot part of the normal equations, once (the reference recomputes it every iteration:
         // Proposed_method_NMSEvsTp.py:63-65)
         CK(launch_pilot_stats(d, nb, io.Xp, ws.pil_m, ws.pil_R, s));
-        CK(launch_gram(d, nb, io.PsiP, d.T_p, ws.pil_R, nullptr, ws.Gp, nullptr, s));
-        CK(launch_rhs_pad(d, nb, io.PsiP, d.T_p, io.Yp, ws.pil_m, nullptr, ws.Gp, nullptr, s));
+        CK(launch_normal_equations(d, nb, io.PsiP, d.T_p, io.Yp, ws.pil_m, ws.pil_R, nullptr, ws.Gp, nullptr, s));
     }
     for (int l = 0; l < d.itera; ++l) {
         int rc = estep_dispatch(d, nb, io.Yd, io.PsiD, io.theta, io.varn, ws.active, ws, ws.stat_m, ws.stat_R,
@@ -133,11 +132,8 @@ static int em_chunk(const Dims& d, int nb, const sbce_io& io, Workspace& ws, cud
         if (rc) return rc;
         {
             PhaseScope ps(SBCE_PHASE_GRAM, s);
-            CK(launch_gram(d, nb, io.PsiD, d.T_d, ws.stat_R, ws.Gp, ws.G, ws.active, s));
-        }
-        {
-            PhaseScope ps(SBCE_PHASE_RHS, s);
-            CK(launch_rhs_pad(d, nb, io.PsiD, d.T_d, io.Yd, ws.stat_m, ws.Gp, ws.G, ws.active, s));
+            CK(launch_normal_equations(d, nb, io.PsiD, d.T_d, io.Yd, ws.stat_m, ws.stat_R, ws.Gp, ws.G, ws.active,
+                                       s));
         }
         {
             PhaseScope ps(SBCE_PHASE_CHOL, s);
@@ -304,10 +300,9 @@ int sbce_mstep(const sbce_cfg* cfg, const sbce_io* io, const double* stat_m, con
         const size_t sb = (size_t)b0 * d.T_d;
         CK(cudaMemsetAsync(ws.stat, 0, (size_t)nb * 4, s));
         CK(launch_pilot_stats(d, nb, o.Xp, ws.pil_m, ws.pil_R, s));
-        CK(launch_gram(d, nb, o.PsiP, d.T_p, ws.pil_R, nullptr, ws.Gp, nullptr, s));
-        CK(launch_rhs_pad(d, nb, o.PsiP, d.T_p, o.Yp, ws.pil_m, nullptr, ws.Gp, nullptr, s));
-        CK(launch_gram(d, nb, o.PsiD, d.T_d, stat_R + sb * d.n_tx * d.n_tx * 2, ws.Gp, ws.G, nullptr, s));
-        CK(launch_rhs_pad(d, nb, o.PsiD, d.T_d, o.Yd, stat_m + sb * d.n_tx * 2, ws.Gp, ws.G, nullptr, s));
+        CK(launch_normal_equations(d, nb, o.PsiP, d.T_p, o.Yp, ws.pil_m, ws.pil_R, nullptr, ws.Gp, nullptr, s));
+        CK(launch_normal_equations(d, nb, o.PsiD, d.T_d, o.Yd, stat_m + sb * d.n_tx * 2,
+                                   stat_R + sb * d.n_tx * d.n_tx * 2, ws.Gp, ws.G, nullptr, s));
         CK(launch_chol_solve(d, nb, ws.G, theta_out + (size_t)b0 * d.L * d.n_rx * 2, nullptr, ws.stat, s));
         if (status) CK(cudaMemcpyAsync(status + b0, ws.stat, (size_t)nb * 4, cudaMemcpyDeviceToDevice, s));
     }

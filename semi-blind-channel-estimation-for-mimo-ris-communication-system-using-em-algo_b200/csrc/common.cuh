@@ -99,10 +99,9 @@ cudaError_t launch_heff_qr(const Dims& d, int nb, const double* Yd, const double
 cudaError_t launch_enum(const Dims& d, int nb, const double* qr, const double* varn, const int32_t* active,
                         double* stat_m, double* stat_R, int32_t* kstar, double* lse_sym, cudaStream_t s);
 // M-step side (mstep.cu)
-cudaError_t launch_gram(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Ginit,
-                        double* Gout, const int32_t* active, cudaStream_t s);
-cudaError_t launch_rhs_pad(const Dims& d, int nb, const double* Psi, int T, const double* Y, const double* sm,
-                           const double* Ginit, double* Gout, const int32_t* active, cudaStream_t s);
+cudaError_t launch_normal_equations(const Dims& d, int nb, const double* Psi, int T, const double* Y,
+                                    const double* sm, const double* sR, const double* Ginit, double* Gout,
+                                    const int32_t* active, cudaStream_t s);
 cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
                               cudaStream_t s);
 // metrics (metrics.cu)

@@ -335,6 +335,7 @@ struct Scan {
     double thr;       // 64 varn^2
     double best, lim; // incumbent distance and enqueue limit best + thr
     int bestk;
+    bool prune;       // skip subtrees whose partial distance already exceeds lim (bit-identical results)
 
     // the M leaves below a node: t0 = residual on row 0, nb = partial distance of the node, code = node digits
     __device__ __forceinline__ void leaf(cplx t0, double nb, int code) {
@@ -373,12 +374,20 @@ struct Scan {
         }
     }
 
+    // Branch and bound.  Every leaf below a node has d2 >= the node's partial distance `base`; once
+    // base > lim (incumbent + 64 varn^2) none of them can improve the arg-min or pass the enqueue test,
+    // so the subtree is "dead": visiting it would change nothing.  Lanes carry a dead flag instead of
+    // returning (the loops contain warp collectives and must stay convergent); a row or subtree is
+    // skipped only when a warp vote says it is dead for all 32 lanes.
+
     // streams S_ ... 1 enumerated with warp-uniform loops
     template <int S_>
-    __device__ __forceinline__ void inner(const cplx (&acc)[NTX], double base, int code, cplx r01) {
+    __device__ __forceinline__ void inner(const cplx (&acc)[NTX], double base, int code, cplx r01, bool dead) {
+        dead = dead || (prune && base > lim);
         if constexpr (S_ == 0) {
-            leaf(acc[0], base, code);
+            if (!dead) leaf(acc[0], base, code);
         } else if constexpr (S_ == 1) {
+            if (__all_sync(0xffffffffu, dead)) return;
             // innermost node level: |u_1|^2 and R_01 x_1 are separable in the in-phase / quadrature indices
             const double* g1 = g + SQM;
             double dI1[SQM], dQ1[SQM];
@@ -390,20 +399,25 @@ struct Scan {
             }
 #pragma unroll 1
             for (int iQ = 0; iQ < SQM; ++iQ) {
+                const double bq = base + dQ1[iQ];
+                const bool deadq = dead || (prune && bq > lim);
+                if (__all_sync(0xffffffffu, deadq)) continue;
                 const double pQ = E::pam(iQ);
                 // t = acc0 - pQ * (i r01) = acc0 - pQ*(-r01.y + i r01.x)
                 const cplx tq = mk(fma(pQ, r01.y, acc[0].x), fma(-pQ, r01.x, acc[0].y));
-                const double bq = base + dQ1[iQ];
                 const int cq = code + ((iQ * SQM) << (E::BITS * (NTX - 2)));
+                if (!deadq) {
 #pragma unroll
-                for (int iI = 0; iI < SQM; ++iI) {
-                    const double pI = E::pam(iI);
-                    const cplx t0 = mk(fma(-pI, r01.x, tq.x), fma(-pI, r01.y, tq.y));
-                    leaf(t0, bq + dI1[iI], cq + (iI << (E::BITS * (NTX - 2))));
+                    for (int iI = 0; iI < SQM; ++iI) {
+                        const double pI = E::pam(iI);
+                        const cplx t0 = mk(fma(-pI, r01.x, tq.x), fma(-pI, r01.y, tq.y));
+                        leaf(t0, bq + dI1[iI], cq + (iI << (E::BITS * (NTX - 2))));
+                    }
                 }
                 maybe_flush();
             }
         } else {
+            if (__all_sync(0xffffffffu, dead)) return;
 #pragma unroll 1
             for (int m = 0; m < M; ++m) {
                 const double* gs = g + S_ * SQM;
@@ -413,16 +427,16 @@ struct Scan {
                 cplx nacc[NTX];
 #pragma unroll
                 for (int i = 0; i < NTX; ++i) nacc[i] = (i < S_) ? csub(acc[i], tab[E::pair(i, S_) * M + m]) : acc[i];
-                inner<S_ - 1>(nacc, nb, code + (m << (E::BITS * (NTX - 1 - S_))), r01);
+                inner<S_ - 1>(nacc, nb, code + (m << (E::BITS * (NTX - 1 - S_))), r01, dead);
             }
         }
     }
 
     // prefix streams (lane-varying digits taken from p), then the uniform inner levels
     template <int S_, int LEFT>
-    __device__ __forceinline__ void prefix(const cplx (&acc)[NTX], double base, int code, int p, cplx r01) {
+    __device__ __forceinline__ void prefix(const cplx (&acc)[NTX], double base, int code, int p, cplx r01, bool dead) {
         if constexpr (LEFT == 0) {
-            inner<S_>(acc, base, code, r01);
+            inner<S_>(acc, base, code, r01, dead);
         } else {
             const int m = (p >> (E::BITS * (LEFT - 1))) & (M - 1);
             const double* gs = g + S_ * SQM;
@@ -432,7 +446,7 @@ struct Scan {
             cplx nacc[NTX];
 #pragma unroll
             for (int i = 0; i < NTX; ++i) nacc[i] = (i < S_) ? csub(acc[i], tab[E::pair(i, S_) * M + m]) : acc[i];
-            prefix<S_ - 1, LEFT - 1>(nacc, nb, code + (m << (E::BITS * (NTX - 1 - S_))), p, r01);
+            prefix<S_ - 1, LEFT - 1>(nacc, nb, code + (m << (E::BITS * (NTX - 1 - S_))), p, r01, dead);
         }
     }
 };
@@ -514,6 +528,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_enum(Dims d, const double* __
     sc.g = g;
     sc.r0 = r00;
     sc.thr = SBCE_THR * s2;
+    sc.prune = (d.flags & SBCE_FLAG_FULL_SCAN) == 0;
     // Babai point (successive slicing): a tight upper bound on min d2 -> incumbent
     {
         cplx acc[NTX];
@@ -541,7 +556,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_enum(Dims d, const double* __
     for (int pb = 0; pb < E::NPREF; pb += 32) {
         const int p = pb + lane;
         const bool valid = p < E::NPREF;
-        sc.template prefix<NTX - 1, E::PL>(yt, valid ? c0 : 1e300, 0, valid ? p : 0, r01);
+        sc.template prefix<NTX - 1, E::PL>(yt, c0, 0, valid ? p : 0, r01, !valid);
     }
 
     // ---- warp merge of the incumbent -------------------------------------------

@@ -14,8 +14,8 @@
 //    arithmetic.  One thread owns one (n >= n') pair of RIS indices and
 //    accumulates the whole n_tx x n_tx block  sum_t conj(psi[t,n]) psi[t,n'] R_t
 //    in registers; psi and R_t chunks are staged in shared memory (R_t reads are
-//    warp-wide broadcasts).  Only the lower triangle is produced.  k_rhs writes
-//    B^H as RP extra rows below the matrix.
+//    warp-wide broadcasts).  Only the lower triangle is produced.  The last CTA
+//    of each trial writes B^H as RP extra rows below the matrix, and the padding.
 //  * k_chol: one CTA per trial, right-looking blocked complex Cholesky (panel
 //    width 16) on the augmented lower trapezoid [G ; B^H]: the triangular solve
 //    of the panel rows turns the B^H rows into (C^-1 B)^H for free, so only the
@@ -24,6 +24,7 @@
 //    tiles.  A non-positive pivot flags the trial (status bit) instead of
 //    poisoning the batch.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -35,16 +36,102 @@ namespace sbce {
 constexpr int GR_THREADS = 256;
 constexpr int GR_TC = 16;  // symbols per shared-memory chunk
 
-// One thread per lower-triangular (n >= n') pair of RIS indices.
+constexpr int RH_MAXR = 8;
+
+// CTAs 0 .. nP-1: one thread per lower-triangular (n >= n') pair of RIS indices.
+// CTA nP (the last one of a trial): the right-hand side rows B^H stored under the matrix,
+//   row Lp + r, column l = n*n_tx + i :  conj(B[l][r]) = sum_t psi[t,n] conj(m_t[i] y_t[r]),
+// one thread per column l with n_rx accumulators, plus the identity padding of the trapezoid.
+// Both kinds of CTA stage the same psi chunks in shared memory.
 template <int NTX>
-__global__ void __launch_bounds__(GR_THREADS) k_gram(Dims d, int T, const cplx* __restrict__ Psi,
-                                                     const cplx* __restrict__ sR, const cplx* __restrict__ Ginit,
+__global__ void __launch_bounds__(GR_THREADS, 2) k_gram(Dims d, int T, const cplx* __restrict__ Psi,
+                                                     const cplx* __restrict__ sR, const cplx* __restrict__ Y,
+                                                     const cplx* __restrict__ sm, const cplx* __restrict__ Ginit,
                                                      cplx* __restrict__ Gout, const int32_t* __restrict__ active) {
     extern __shared__ double2 gsm[];
     const int b = blockIdx.y;
     if (active != nullptr && active[b] == 0) return;
     const int N1 = d.N1;
     const int P = N1 * (N1 + 1) / 2;
+    cplx* sPsi = gsm;               // [GR_TC][N1]
+    cplx* sRr = sPsi + GR_TC * N1;  // [GR_TC][NTX*NTX]  (rhs CTA: [GR_TC][NTX][n_rx] conj(m_i y_r))
+    const cplx* psi_b = Psi + (size_t)(d.psi_shared ? 0 : b) * T * N1;
+    const size_t gstride = (size_t)d.Ltot * d.Lp;
+    cplx* Gb = Gout + (size_t)b * gstride;
+    const cplx* Gi = Ginit ? Ginit + (size_t)b * gstride : nullptr;
+
+    if (blockIdx.x == gridDim.x - 1) {
+        // ---------------- right-hand side rows + padding
+        const int n_rx = d.n_rx, L = d.L;
+        const cplx* m_b = sm + (size_t)b * T * NTX;
+        const cplx* y_b = Y + (size_t)b * T * n_rx;
+        // each thread owns columns l and l + GR_THREADS of a 2*GR_THREADS-wide pass (one pass for L <= 512)
+        for (int l0 = 0; l0 < L; l0 += 2 * GR_THREADS) {
+            int ls[2], ns[2], is[2];
+            bool have[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                ls[u] = l0 + u * GR_THREADS + threadIdx.x;
+                have[u] = ls[u] < L;
+                ns[u] = have[u] ? ls[u] / NTX : 0;
+                is[u] = have[u] ? ls[u] % NTX : 0;
+            }
+            cplx acc[2][RH_MAXR];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int r = 0; r < RH_MAXR; ++r) acc[u][r] = mk(0.0, 0.0);
+            for (int t0 = 0; t0 < T; t0 += GR_TC) {
+                const int tc = min(GR_TC, T - t0);
+                __syncthreads();
+                for (int e = threadIdx.x; e < tc * N1; e += GR_THREADS) sPsi[e] = psi_b[(size_t)t0 * N1 + e];
+                for (int e = threadIdx.x; e < tc * NTX * n_rx; e += GR_THREADS) {
+                    const int tt = e / (NTX * n_rx), ii = (e / n_rx) % NTX, r = e % n_rx;
+                    sRr[e] = cconj(cmul(m_b[(size_t)(t0 + tt) * NTX + ii], y_b[(size_t)(t0 + tt) * n_rx + r]));
+                }
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (have[u]) {
+                        for (int tt = 0; tt < tc; ++tt) {
+                            const cplx p = sPsi[tt * N1 + ns[u]];
+                            const cplx* z = sRr + (tt * NTX + is[u]) * n_rx;
+#pragma unroll
+                            for (int r = 0; r < RH_MAXR; ++r)
+                                if (r < n_rx) cfma(acc[u][r], p, z[r]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (have[u]) {
+#pragma unroll
+                    for (int r = 0; r < RH_MAXR; ++r)
+                        if (r < n_rx) {
+                            const size_t o = (size_t)(d.Lp + r) * d.Lp + ls[u];
+                            cplx v = acc[u][r];
+                            if (Gi) v = cadd(v, Gi[o]);
+                            Gb[o] = v;
+                        }
+                }
+            }
+        }
+        // padding: identity on the padded diagonal rows L..Lp-1, zero padded columns / rows of B^H
+        const int padrows = (d.Lp - d.L) + d.RP;
+        for (int e = threadIdx.x; e < padrows * d.Lp; e += GR_THREADS) {
+            const int pr = e / d.Lp, c = e % d.Lp;
+            if (pr < d.Lp - d.L) {
+                const int row = d.L + pr;
+                Gb[(size_t)row * d.Lp + c] = (c == row) ? mk(1.0, 0.0) : mk(0.0, 0.0);
+            } else {
+                const int r = pr - (d.Lp - d.L);
+                if (r >= d.n_rx || c >= d.L) Gb[(size_t)(d.Lp + r) * d.Lp + c] = mk(0.0, 0.0);
+            }
+        }
+        return;
+    }
+
     const int item = blockIdx.x * GR_THREADS + threadIdx.x;
     const bool is_pair = item < P;
     int n = 0, np = 0;
@@ -55,154 +142,122 @@ __global__ void __launch_bounds__(GR_THREADS) k_gram(Dims d, int T, const cplx* 
         np = item - n * (n + 1) / 2;
     }
 
-    cplx* sPsi = gsm;               // [GR_TC][N1]
-    cplx* sRr = sPsi + GR_TC * N1;  // [GR_TC][NTX*NTX]
-
-    cplx acc[NTX][NTX];
+    // R_t is Hermitian: only its real diagonal and its upper triangle are used.  For i<j the two block
+    // entries  acc[i][j] += p R_ij  and  acc[j][i] += p conj(R_ij)  share their four real products, so we
+    // accumulate U = sum pr Rr, V = sum pi Ri, W = sum pr Ri, Z = sum pi Rr (4 FMAs instead of 8) and
+    // combine at the end:  acc[i][j] = (U - V, W + Z),  acc[j][i] = (U + V, Z - W).
+    constexpr int NPAIR = NTX * (NTX - 1) / 2;
+    constexpr int NPAIR1 = NPAIR > 0 ? NPAIR : 1;
+    constexpr int DP = (NTX + 1) & ~1;            // diagonal reals, padded to keep the complex part 16-B aligned
+    constexpr int RST = DP + 2 * NPAIR;           // doubles per symbol in the staged R chunk
+    double* sRd = (double*)sRr;                   // [GR_TC][RST]
+    double dg_re[NTX], dg_im[NTX];
+    double U[NPAIR1], V[NPAIR1], W[NPAIR1], Z[NPAIR1];
 #pragma unroll
-    for (int i = 0; i < NTX; ++i)
+    for (int i = 0; i < NTX; ++i) { dg_re[i] = 0.0; dg_im[i] = 0.0; }
 #pragma unroll
-        for (int j = 0; j < NTX; ++j) acc[i][j] = mk(0.0, 0.0);
+    for (int q = 0; q < NPAIR1; ++q) { U[q] = 0.0; V[q] = 0.0; W[q] = 0.0; Z[q] = 0.0; }
 
-    const cplx* psi_b = Psi + (size_t)(d.psi_shared ? 0 : b) * T * N1;
     const cplx* R_b = sR + (size_t)b * T * NTX * NTX;
 
     for (int t0 = 0; t0 < T; t0 += GR_TC) {
         const int tc = min(GR_TC, T - t0);
         __syncthreads();
         for (int e = threadIdx.x; e < tc * N1; e += GR_THREADS) sPsi[e] = psi_b[(size_t)t0 * N1 + e];
-        for (int e = threadIdx.x; e < tc * NTX * NTX; e += GR_THREADS) sRr[e] = R_b[(size_t)t0 * NTX * NTX + e];
+        for (int e = threadIdx.x; e < tc * NTX * NTX; e += GR_THREADS) {
+            const int tt = e / (NTX * NTX), i = (e / NTX) % NTX, j = e % NTX;
+            if (j >= i) {
+                const cplx v = R_b[(size_t)t0 * NTX * NTX + e];
+                if (i == j) sRd[tt * RST + i] = v.x;
+                else {
+                    const int q = i * NTX - i * (i + 1) / 2 + (j - i - 1);  // upper-triangle pair index
+                    sRd[tt * RST + DP + 2 * q] = v.x;
+                    sRd[tt * RST + DP + 2 * q + 1] = v.y;
+                }
+            }
+        }
         __syncthreads();
         if (is_pair) {
+#pragma unroll 2
             for (int tt = 0; tt < tc; ++tt) {
                 const cplx a = sPsi[tt * N1 + n];
                 const cplx c = sPsi[tt * N1 + np];
                 const cplx p = cmulc(c, a);  // conj(psi[t,n]) psi[t,n']
-                const cplx* Rt = sRr + tt * NTX * NTX;
+                const double* Rt = sRd + tt * RST;
 #pragma unroll
-                for (int i = 0; i < NTX; ++i)
+                for (int i = 0; i < NTX; ++i) {
+                    const double r = Rt[i];
+                    dg_re[i] = fma(p.x, r, dg_re[i]);
+                    dg_im[i] = fma(p.y, r, dg_im[i]);
+                }
+                const cplx* Ru = (const cplx*)(Rt + DP);
 #pragma unroll
-                    for (int j = 0; j < NTX; ++j) cfma(acc[i][j], p, Rt[i * NTX + j]);
+                for (int q = 0; q < NPAIR; ++q) {
+                    const cplx r = Ru[q];
+                    U[q] = fma(p.x, r.x, U[q]);
+                    V[q] = fma(p.y, r.y, V[q]);
+                    W[q] = fma(p.x, r.y, W[q]);
+                    Z[q] = fma(p.y, r.x, Z[q]);
+                }
             }
         }
     }
     if (is_pair) {
-        const size_t gstride = (size_t)d.Ltot * d.Lp;
-        cplx* Gb = Gout + (size_t)b * gstride;
-        const cplx* Gi = Ginit ? Ginit + (size_t)b * gstride : nullptr;
+        auto put = [&](int i, int j, cplx v) {
+            const size_t o = (size_t)(n * NTX + i) * d.Lp + (np * NTX + j);
+            if (Gi) v = cadd(v, Gi[o]);
+            Gb[o] = v;
+        };
+#pragma unroll
+        for (int i = 0; i < NTX; ++i) put(i, i, mk(dg_re[i], dg_im[i]));
 #pragma unroll
         for (int i = 0; i < NTX; ++i)
 #pragma unroll
-            for (int j = 0; j < NTX; ++j) {
-                const size_t o = (size_t)(n * NTX + i) * d.Lp + (np * NTX + j);
-                cplx v = acc[i][j];
-                if (Gi) v = cadd(v, Gi[o]);
-                Gb[o] = v;
+            for (int j = i + 1; j < NTX; ++j) {
+                const int q = i * NTX - i * (i + 1) / 2 + (j - i - 1);
+                put(i, j, mk(U[q] - V[q], W[q] + Z[q]));
+                put(j, i, mk(U[q] + V[q], Z[q] - W[q]));
             }
     }
 }
 
-// Right-hand side rows (general n_rx): thread per (n, i, r)
-__global__ void k_rhs(Dims d, int T, const cplx* __restrict__ Psi, const cplx* __restrict__ Y,
-                      const cplx* __restrict__ sm, const cplx* __restrict__ Ginit, cplx* __restrict__ Gout,
-                      const int32_t* __restrict__ active) {
-    const int b = blockIdx.y;
-    if (active != nullptr && active[b] == 0) return;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = d.N1 * d.n_tx * d.n_rx;
-    if (e >= total) return;
-    const int r = e % d.n_rx, l = e / d.n_rx, i = l % d.n_tx, n = l / d.n_tx;
-    const cplx* psi_b = Psi + (size_t)(d.psi_shared ? 0 : b) * T * d.N1;
-    const cplx* m_b = sm + (size_t)b * T * d.n_tx;
-    const cplx* y_b = Y + (size_t)b * T * d.n_rx;
-    cplx acc = mk(0.0, 0.0);
-    for (int t = 0; t < T; ++t) {
-        const cplx z = cmul(m_b[(size_t)t * d.n_tx + i], y_b[(size_t)t * d.n_rx + r]);  // m_i y_r
-        cfmac(acc, psi_b[(size_t)t * d.N1 + n], z);                                     // psi * conj(m y)
-    }
-    const size_t gstride = (size_t)d.Ltot * d.Lp;
-    const size_t o = (size_t)(d.Lp + r) * d.Lp + l;
-    if (Ginit) acc = cadd(acc, Ginit[(size_t)b * gstride + o]);
-    Gout[(size_t)b * gstride + o] = acc;
-}
-
-// padding rows/cols (identity on the padded diagonal, zero B^H padding rows)
-__global__ void k_pad(Dims d, cplx* __restrict__ Gout, const int32_t* __restrict__ active) {
-    const int b = blockIdx.y;
-    if (active != nullptr && active[b] == 0) return;
-    cplx* Gb = Gout + (size_t)b * d.Ltot * d.Lp;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    // padded matrix rows L..Lp-1 (all columns), padded columns L..Lp-1 of the B^H rows, padded B^H rows
-    const int padrows = (d.Lp - d.L) + d.RP;
-    if (e >= padrows * d.Lp) return;
-    const int pr = e / d.Lp, c = e % d.Lp;
-    int row;
-    if (pr < d.Lp - d.L) {
-        row = d.L + pr;
-        Gb[(size_t)row * d.Lp + c] = (c == row) ? mk(1.0, 0.0) : mk(0.0, 0.0);
-    } else {
-        const int r = pr - (d.Lp - d.L);
-        row = d.Lp + r;
-        if (r >= d.n_rx || c >= d.L) Gb[(size_t)row * d.Lp + c] = mk(0.0, 0.0);
-    }
-}
-
 template <int NTX>
-static cudaError_t run_gram(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Ginit,
-                            double* Gout, const int32_t* active, cudaStream_t s) {
+static cudaError_t run_gram(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Y,
+                            const double* sm, const double* Ginit, double* Gout, const int32_t* active,
+                            cudaStream_t s) {
     const int P = d.N1 * (d.N1 + 1) / 2;
-    dim3 grid((P + GR_THREADS - 1) / GR_THREADS, nb);
-    size_t smem = sizeof(cplx) * (size_t)(GR_TC * d.N1 + GR_TC * NTX * NTX);
+    dim3 grid((P + GR_THREADS - 1) / GR_THREADS + 1, nb);   // + 1: the right-hand-side / padding CTA
+    const int zsz = NTX * (d.n_rx > NTX ? d.n_rx : NTX);
+    size_t smem = sizeof(cplx) * (size_t)(GR_TC * d.N1 + GR_TC * zsz);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_gram<NTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_gram<NTX><<<grid, GR_THREADS, smem, s>>>(d, T, (const cplx*)Psi, (const cplx*)sR, (const cplx*)Ginit,
-                                               (cplx*)Gout, active);
+    k_gram<NTX><<<grid, GR_THREADS, smem, s>>>(d, T, (const cplx*)Psi, (const cplx*)sR, (const cplx*)Y,
+                                               (const cplx*)sm, (const cplx*)Ginit, (cplx*)Gout, active);
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_gram(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Ginit,
-                        double* Gout, const int32_t* active, cudaStream_t s) {
+// Normal-equation build: lower triangle of G, B^H rows and padding, one launch.
+cudaError_t launch_normal_equations(const Dims& d, int nb, const double* Psi, int T, const double* Y,
+                                    const double* sm, const double* sR, const double* Ginit, double* Gout,
+                                    const int32_t* active, cudaStream_t s) {
+    if (d.n_rx > RH_MAXR) return cudaErrorInvalidValue;
     switch (d.n_tx) {
-        case 1: return run_gram<1>(d, nb, Psi, T, sR, Ginit, Gout, active, s);
-        case 2: return run_gram<2>(d, nb, Psi, T, sR, Ginit, Gout, active, s);
-        case 3: return run_gram<3>(d, nb, Psi, T, sR, Ginit, Gout, active, s);
-        case 4: return run_gram<4>(d, nb, Psi, T, sR, Ginit, Gout, active, s);
+        case 1: return run_gram<1>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
+        case 2: return run_gram<2>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
+        case 3: return run_gram<3>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
+        case 4: return run_gram<4>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
         default: return cudaErrorInvalidValue;
     }
-}
-
-cudaError_t launch_rhs_pad(const Dims& d, int nb, const double* Psi, int T, const double* Y, const double* sm,
-                           const double* Ginit, double* Gout, const int32_t* active, cudaStream_t s) {
-    cudaError_t e;
-    {
-        const int total = d.N1 * d.n_tx * d.n_rx;
-        dim3 grid((total + 127) / 128, nb);
-        k_rhs<<<grid, 128, 0, s>>>(d, T, (const cplx*)Psi, (const cplx*)Y, (const cplx*)sm, (const cplx*)Ginit,
-                                   (cplx*)Gout, active);
-        count_launch();
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
-    {
-        const int padrows = (d.Lp - d.L) + d.RP;
-        dim3 grid((padrows * d.Lp + 127) / 128, nb);
-        k_pad<<<grid, 128, 0, s>>>(d, (cplx*)Gout, active);
-        count_launch();
-        e = cudaGetLastError();
-    }
-    return e;
 }
 
 // ---------------------------------------------------------------------------
 // Blocked Cholesky of the augmented trapezoid + back substitution
 // ---------------------------------------------------------------------------
-constexpr int CH_THREADS = 256;
-constexpr int CH_WARPS = CH_THREADS / 32;
 constexpr int CH_NB = 16;            // panel width
-constexpr int CH_SP = CH_NB + 1;     // row stride (complex) of the shared panel: odd -> conflict-free column walks
+constexpr int CH_DS = CH_NB + 1;     // row stride (complex) of the shared 16x16 blocks
 
 __device__ __forceinline__ void dmma16x8x8(double (&c)[4], const double (&a)[4], double b0, double b1) {
     asm volatile(
@@ -211,17 +266,24 @@ __device__ __forceinline__ void dmma16x8x8(double (&c)[4], const double (&a)[4],
         : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b0), "d"(b1));
 }
 
-// LEFT-looking blocked complex Cholesky on the FP64 tensor path (mma.sync m16n8k8.f64, "DMMA"):
-// panel k (16 columns, all rows below its diagonal block) is brought up to date with ALL previous
-// panels in one register-accumulated product
-//   S[r][c] = A[r][c] - sum_{q<k0} C[r][q] conj(C[k0+c][q])
-// Each warp owns 16-row tiles of the panel; the operand fragments are loaded straight from the
-// factor in global memory (L2 / L1 resident, 16-byte complex loads in fragment order, no shared
-// staging), 8 DMMAs per 8 previous columns.  The updated panel goes to shared memory, its diagonal
-// block is factored by one warp, the rows below are solved by forward substitution (thread per
-// row) and the panel is written once; the trailing matrix is never rewritten.
-__global__ void __launch_bounds__(CH_THREADS, 2) k_chol(Dims d, cplx* __restrict__ Gall, cplx* __restrict__ theta,
-                                                        const int32_t* __restrict__ active, int32_t* __restrict__ stat) {
+// LEFT-looking blocked complex Cholesky on the FP64 tensor path (mma.sync m16n8k8.f64, SASS DMMA).
+// Per 16-column panel k, three phases separated by CTA barriers:
+//   1. every warp brings its 16-row tiles up to date with ALL previous panels in one
+//      register-accumulated product   S = A - C[rows, 0:k0] * C[k0:k0+16, 0:k0]^H
+//      (operand fragments are 16-byte complex loads straight from the L2/L1-resident factor,
+//      8 DMMAs per 8 previous columns) and writes S back in place;
+//   2. warp 0 factors the 16x16 diagonal block D and forms W = D^-1 in shared memory;
+//   3. every warp finishes its tiles below the diagonal block with one more product X = S W^H
+//      (16 DMMAs per tile) -- the triangular solve as a tensor-core GEMM -- and writes X once.
+// The trailing matrix is never touched; the B^H rows carried under the matrix come out as
+// (C^-1 B)^H, i.e. the forward substitution is free.  Only 9 KB of shared memory per CTA, so four
+// CTAs (trials) share an SM and overlap each other's serial phase 2.
+template <int CH_THREADS, int CH_MINB>
+__global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol(Dims d, cplx* __restrict__ Gall,
+                                                              cplx* __restrict__ theta,
+                                                              const int32_t* __restrict__ active,
+                                                              int32_t* __restrict__ stat) {
+    constexpr int CH_WARPS = CH_THREADS / 32;
     extern __shared__ double2 csm[];
     const int b = blockIdx.x;
     if (active != nullptr && active[b] == 0) return;
@@ -230,8 +292,9 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(Dims d, cplx* __restrict
     const int Lp = d.Lp, Ltot = d.Ltot, ld = d.Lp;
     cplx* A = Gall + (size_t)b * Ltot * Lp;
 
-    cplx* sD = csm;                            // [CH_NB][CH_NB+1] diagonal block / its factor (also reduction scratch)
-    cplx* buf = sD + 2 * CH_NB * (CH_NB + 1);  // updated panel [rows][CH_SP]; later theta
+    cplx* sD = csm;                   // [16][17] diagonal block factor (later: reduction scratch)
+    cplx* sW = sD + CH_NB * CH_DS;    // [16][17] its inverse
+    cplx* th = sW + CH_NB * CH_DS;    // [Lp][n_rx] solution during the back substitution
     __shared__ int s_bad;
     if (tid == 0) s_bad = 0;
 
@@ -239,60 +302,62 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(Dims d, cplx* __restrict
         const int nb = min(CH_NB, Lp - k0);   // multiple of 4
         const int rows = Ltot - k0;           // rows of the panel including its diagonal block
         const int nrt = (rows + 15) >> 4;
-        __syncthreads();                      // previous panel fully written (global) and buf free
-        for (int rt = warp; rt < nrt; rt += CH_WARPS) {
-            const int r0 = rt << 4;
-            // accumulators: [n-tile][c0..c3], real and imaginary parts
-            double cr[2][4], ci[2][4];
+        __syncthreads();                      // previous panel fully written
+        // ---- phase 1: S = A - C_prev C_rows^H for every 16-row tile
+        if (k0 > 0) {
+            for (int rt = warp; rt < nrt; rt += CH_WARPS) {
+                const int r0 = rt << 4;
+                double cr[2][4], ci[2][4];
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { cr[j][e] = 0.0; ci[j][e] = 0.0; }
-            const int ra = min(r0 + g, rows - 1), rb8 = min(r0 + g + 8, rows - 1);
-            const cplx* pa0 = A + (size_t)(k0 + ra) * ld + tig;
-            const cplx* pa1 = A + (size_t)(k0 + rb8) * ld + tig;
-            const cplx* pb0 = A + (size_t)min(k0 + g, Ltot - 1) * ld + tig;
-            const cplx* pb1 = A + (size_t)min(k0 + 8 + g, Ltot - 1) * ld + tig;
+                    for (int e = 0; e < 4; ++e) { cr[j][e] = 0.0; ci[j][e] = 0.0; }
+                const int ra = min(r0 + g, rows - 1), rb8 = min(r0 + g + 8, rows - 1);
+                const cplx* pa0 = A + (size_t)(k0 + ra) * ld + tig;
+                const cplx* pa1 = A + (size_t)(k0 + rb8) * ld + tig;
+                const cplx* pb0 = A + (size_t)min(k0 + g, Ltot - 1) * ld + tig;
+                const cplx* pb1 = A + (size_t)min(k0 + 8 + g, Ltot - 1) * ld + tig;
 #pragma unroll 2
-            for (int q0 = 0; q0 < k0; q0 += 8) {
-                const cplx a0 = pa0[q0], a1 = pa1[q0], a2 = pa0[q0 + 4], a3 = pa1[q0 + 4];
-                const cplx b00 = pb0[q0], b01 = pb0[q0 + 4], b10 = pb1[q0], b11 = pb1[q0 + 4];
-                const double ar[4] = {a0.x, a1.x, a2.x, a3.x};
-                const double ai[4] = {a0.y, a1.y, a2.y, a3.y};
-                // sum_q a conj(b):  re += ar br + ai bi ;  im += ai br - ar bi
-                dmma16x8x8(cr[0], ar, b00.x, b01.x);
-                dmma16x8x8(cr[0], ai, b00.y, b01.y);
-                dmma16x8x8(ci[0], ai, b00.x, b01.x);
-                dmma16x8x8(ci[0], ar, -b00.y, -b01.y);
-                dmma16x8x8(cr[1], ar, b10.x, b11.x);
-                dmma16x8x8(cr[1], ai, b10.y, b11.y);
-                dmma16x8x8(ci[1], ai, b10.x, b11.x);
-                dmma16x8x8(ci[1], ar, -b10.y, -b11.y);
-            }
-            // S = A - acc  -> shared panel (fragment: rows g / g+8, columns 8j + 2 tig + {0,1})
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int lr = r0 + g + 8 * h;
-                    const int c = 8 * j + 2 * tig;
-                    if (lr < rows && c < nb) {
-                        const cplx* src = A + (size_t)(k0 + lr) * ld + k0 + c;
-                        const cplx v0 = src[0], v1 = src[1];
-                        buf[lr * CH_SP + c] = mk(v0.x - cr[j][2 * h], v0.y - ci[j][2 * h]);
-                        buf[lr * CH_SP + c + 1] = mk(v1.x - cr[j][2 * h + 1], v1.y - ci[j][2 * h + 1]);
-                    }
+                for (int q0 = 0; q0 < k0; q0 += 8) {
+                    const cplx a0 = pa0[q0], a1 = pa1[q0], a2 = pa0[q0 + 4], a3 = pa1[q0 + 4];
+                    const cplx b00 = pb0[q0], b01 = pb0[q0 + 4], b10 = pb1[q0], b11 = pb1[q0 + 4];
+                    const double ar[4] = {a0.x, a1.x, a2.x, a3.x};
+                    const double ai[4] = {a0.y, a1.y, a2.y, a3.y};
+                    // sum_q a conj(b):  re += ar br + ai bi ;  im += ai br - ar bi
+                    dmma16x8x8(cr[0], ar, b00.x, b01.x);
+                    dmma16x8x8(cr[0], ai, b00.y, b01.y);
+                    dmma16x8x8(ci[0], ai, b00.x, b01.x);
+                    dmma16x8x8(ci[0], ar, -b00.y, -b01.y);
+                    dmma16x8x8(cr[1], ar, b10.x, b11.x);
+                    dmma16x8x8(cr[1], ai, b10.y, b11.y);
+                    dmma16x8x8(ci[1], ai, b10.x, b11.x);
+                    dmma16x8x8(ci[1], ar, -b10.y, -b11.y);
                 }
+                // in place: fragment rows g / g+8, columns 8j + 2 tig + {0,1}
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int lr = r0 + g + 8 * h;
+                        const int c = 8 * j + 2 * tig;
+                        if (lr < rows && c < nb) {
+                            cplx* p2 = A + (size_t)(k0 + lr) * ld + k0 + c;
+                            const cplx v0 = p2[0], v1 = p2[1];
+                            p2[0] = mk(v0.x - cr[j][2 * h], v0.y - ci[j][2 * h]);
+                            p2[1] = mk(v1.x - cr[j][2 * h + 1], v1.y - ci[j][2 * h + 1]);
+                        }
+                    }
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        // ---- diagonal block (local rows 0..nb) -> sD, unblocked Cholesky by warp 0 (lane = row)
-        if (tid < 32) {
-            const int r = tid;
-            if (r < nb)
-                for (int c = 0; c < nb; ++c) sD[r * (CH_NB + 1) + c] = (c <= r) ? buf[r * CH_SP + c] : mk(0.0, 0.0);
+        // ---- phase 2: diagonal block -> sD, unblocked Cholesky by warp 0 (lane = row), W = D^-1
+        if (warp == 0) {
+            const int r = lane;
+            for (int c = 0; c < CH_NB; ++c)
+                if (r < CH_NB) sD[r * CH_DS + c] = (r < nb && c <= r && c < nb) ? A[(size_t)(k0 + r) * ld + k0 + c] : mk(0.0, 0.0);
             __syncwarp();
             for (int c = 0; c < nb; ++c) {
-                double piv = sD[c * (CH_NB + 1) + c].x;
+                double piv = sD[c * CH_DS + c].x;
                 if (!(piv > 0.0)) {
                     if (r == 0) s_bad = 1;
                     piv = 1.0;
@@ -300,84 +365,142 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(Dims d, cplx* __restrict
                 const double dg = sqrt(piv);
                 const double inv = 1.0 / dg;
                 __syncwarp();
-                if (r == c) sD[c * (CH_NB + 1) + c] = mk(dg, 0.0);
-                if (r > c && r < nb) sD[r * (CH_NB + 1) + c] = cscale(sD[r * (CH_NB + 1) + c], inv);
+                if (r == c) sD[c * CH_DS + c] = mk(dg, 0.0);
+                if (r > c && r < nb) sD[r * CH_DS + c] = cscale(sD[r * CH_DS + c], inv);
                 __syncwarp();
                 if (r > c && r < nb) {
-                    const cplx lrc = sD[r * (CH_NB + 1) + c];
-                    for (int q = c + 1; q <= r; ++q) cfmsc(sD[r * (CH_NB + 1) + q], lrc, sD[q * (CH_NB + 1) + c]);
+                    const cplx lrc = sD[r * CH_DS + c];
+                    for (int q = c + 1; q <= r; ++q) cfmsc(sD[r * CH_DS + q], lrc, sD[q * CH_DS + c]);
                 }
                 __syncwarp();
             }
+            // W = D^-1 (lower triangular), lane = column; rows/cols >= nb are zero
+            if (r < CH_NB) {
+                const int c = r;
+                for (int i = 0; i < CH_NB; ++i) {
+                    cplx v = mk(0.0, 0.0);
+                    if (c < nb && i < nb) {
+                        if (i == c) v = mk(1.0 / sD[i * CH_DS + i].x, 0.0);
+                        else if (i > c) {
+                            cplx a0 = mk(0.0, 0.0), a1 = mk(0.0, 0.0);
+                            int q = c;
+                            for (; q + 1 < i; q += 2) {
+                                cfma(a0, sD[i * CH_DS + q], sW[q * CH_DS + c]);
+                                cfma(a1, sD[i * CH_DS + q + 1], sW[(q + 1) * CH_DS + c]);
+                            }
+                            if (q < i) cfma(a0, sD[i * CH_DS + q], sW[q * CH_DS + c]);
+                            const double invd = -1.0 / sD[i * CH_DS + i].x;
+                            v = mk((a0.x + a1.x) * invd, (a0.y + a1.y) * invd);
+                        }
+                    }
+                    sW[i * CH_DS + c] = v;
+                }
+            }
+            __syncwarp();
+            // factored diagonal block back to global
+            for (int e = lane; e < nb * nb; e += 32) {
+                const int rr = e / nb, c = e % nb;
+                if (c <= rr) A[(size_t)(k0 + rr) * ld + k0 + c] = sD[rr * CH_DS + c];
+            }
         }
         __syncthreads();
-        // ---- write the factored diagonal block; rows below: forward substitution X D^H = S (thread per row)
-        for (int e = tid; e < nb * nb; e += CH_THREADS) {
-            const int r = e / nb, c = e % nb;
-            if (c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = sD[r * (CH_NB + 1) + c];
-        }
-        for (int lr = nb + tid; lr < rows; lr += CH_THREADS) {
-            cplx* xr = buf + lr * CH_SP;  // the row is solved in place in shared memory
-            cplx* dst = A + (size_t)(k0 + lr) * ld + k0;
-            for (int c = 0; c < nb; ++c) {
-                cplx v = xr[c];
-                const cplx* dc = sD + c * (CH_NB + 1);
-                for (int q = 0; q < c; ++q) cfmsc(v, xr[q], dc[q]);  // v -= x_q conj(D[c][q])
-                v = cscale(v, 1.0 / dc[c].x);
-                xr[c] = v;
-                dst[c] = v;
+        // ---- phase 3: rows below the diagonal block: X = S W^H, i.e. X[r][c] = sum_q S[r][q] conj(W[c][q])
+        // local row tiles start at local row nb (nb < 16 only in the last panel, where the tile grid shifts)
+        {
+            const int rows3 = rows - nb;
+            const int nrt3 = (rows3 + 15) >> 4;
+            for (int rt = warp; rt < nrt3; rt += CH_WARPS) {
+                const int r0 = nb + (rt << 4);
+                const int ra = min(r0 + g, rows - 1), rb8 = min(r0 + g + 8, rows - 1);
+                const cplx* pa0 = A + (size_t)(k0 + ra) * ld + k0 + tig;
+                const cplx* pa1 = A + (size_t)(k0 + rb8) * ld + k0 + tig;
+                double cr[2][4], ci[2][4];
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { cr[j][e] = 0.0; ci[j][e] = 0.0; }
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    // columns q = 8kk + tig, +4 of S (zero beyond nb: they were never part of this panel)
+                    const int q0 = 8 * kk + tig;
+                    cplx a0 = mk(0, 0), a1 = mk(0, 0), a2 = mk(0, 0), a3 = mk(0, 0);
+                    if (q0 < nb) { a0 = pa0[8 * kk]; a1 = pa1[8 * kk]; }
+                    if (q0 + 4 < nb) { a2 = pa0[8 * kk + 4]; a3 = pa1[8 * kk + 4]; }
+                    const double ar[4] = {a0.x, a1.x, a2.x, a3.x};
+                    const double ai[4] = {a0.y, a1.y, a2.y, a3.y};
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        // B[k=q][n=c] = conj(W[c][q]), c = 8j + g, q = 8kk + tig (+4)
+                        const cplx w0 = sW[(8 * j + g) * CH_DS + 8 * kk + tig];
+                        const cplx w1 = sW[(8 * j + g) * CH_DS + 8 * kk + tig + 4];
+                        dmma16x8x8(cr[j], ar, w0.x, w1.x);
+                        dmma16x8x8(cr[j], ai, w0.y, w1.y);
+                        dmma16x8x8(ci[j], ai, w0.x, w1.x);
+                        dmma16x8x8(ci[j], ar, -w0.y, -w1.y);
+                    }
+                }
+                __syncwarp();  // all lanes have read S before anyone overwrites it
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int lr = r0 + g + 8 * h;
+                        const int c = 8 * j + 2 * tig;
+                        if (lr < rows && c < nb) {
+                            cplx* p2 = A + (size_t)(k0 + lr) * ld + k0 + c;
+                            p2[0] = mk(cr[j][2 * h], ci[j][2 * h]);
+                            p2[1] = mk(cr[j][2 * h + 1], ci[j][2 * h + 1]);
+                        }
+                    }
             }
         }
     }
-    cplx* Ps = buf;
     __syncthreads();
     if (tid == 0 && s_bad && stat) atomicOr(&stat[b], SBCE_ST_NOT_PD);
 
     // ---- back substitution  C^H theta = z,  z[l][r] = conj(A[Lp + r][l])
-    // theta kept in shared (reuse Ps): th[l * RPp + r]
+    // Column-oriented ("right-looking"): blocks from the bottom up; once the 16 unknowns of a block are
+    // known, every earlier right-hand-side entry c < k0 is updated with the block's 16 factor rows --
+    // those rows are contiguous in memory, so consecutive threads read consecutive columns (coalesced)
+    // and each thread has 16 independent loads in flight.
     const int nrx = d.n_rx;
-    cplx* th = Ps;
     for (int e = tid; e < Lp * nrx; e += CH_THREADS) {
         const int l = e / nrx, r = e % nrx;
         th[e] = cconj(A[(size_t)(Lp + r) * ld + l]);
     }
-    __syncthreads();
     for (int k0 = ((Lp - 1) / CH_NB) * CH_NB; k0 >= 0; k0 -= CH_NB) {
         const int nb = min(CH_NB, Lp - k0);
-        const int c1 = k0 + nb;
-        // th[k0+c][r] -= sum_{row >= c1} conj(A[row][k0+c]) th[row][r]
-        const int nout = nb * nrx;
-        // split rows among CH_THREADS/nout groups (nout <= 128)
-        const int groups = max(1, CH_THREADS / nout);
-        cplx part = mk(0.0, 0.0);
-        const int o = tid % nout, gidx = tid / nout;
-        if (gidx < groups) {
-            const int c = o / nrx, r = o % nrx;
-            for (int row = c1 + gidx; row < Lp; row += groups) cfmac(part, th[row * nrx + r], A[(size_t)row * ld + k0 + c]);
-        }
-        // reduce partial sums through shared sD/sW area (>= 2*16*17 cplx = 544)
-        cplx* red = sD;
-        __syncthreads();
-        if (gidx < groups) red[gidx * nout + o] = part;
-        __syncthreads();
-        if (tid < nout) {
-            cplx sum = mk(0.0, 0.0);
-            for (int gq = 0; gq < groups; ++gq) sum = cadd(sum, red[gq * nout + tid]);
-            th[(k0 + tid / nrx) * nrx + (tid % nrx)] = csub(th[(k0 + tid / nrx) * nrx + (tid % nrx)], sum);
+        __syncthreads();  // th updates of the previous block are complete
+        for (int e = tid; e < nb * nb; e += CH_THREADS) {
+            const int r = e / nb, c = e % nb;
+            sD[r * CH_DS + c] = (c <= r) ? A[(size_t)(k0 + r) * ld + k0 + c] : mk(0.0, 0.0);
         }
         __syncthreads();
-        // solve the nb x nb upper-triangular system D^H x = rhs sequentially (one thread per rhs column)
+        // D^H x = rhs, upper triangular, one thread per right-hand side
         if (tid < nrx) {
             const int r = tid;
             for (int c = nb - 1; c >= 0; --c) {
                 cplx v = th[(k0 + c) * nrx + r];
-                for (int q = c + 1; q < nb; ++q) cfmsc(v, th[(k0 + q) * nrx + r], A[(size_t)(k0 + q) * ld + k0 + c]);
-                const double invd = 1.0 / A[(size_t)(k0 + c) * ld + k0 + c].x;
-                th[(k0 + c) * nrx + r] = cscale(v, invd);
+                for (int q = c + 1; q < nb; ++q) cfmsc(v, th[(k0 + q) * nrx + r], sD[q * CH_DS + c]);
+                th[(k0 + c) * nrx + r] = cscale(v, 1.0 / sD[c * CH_DS + c].x);
             }
         }
         __syncthreads();
+        // th[c][:] -= sum_q conj(C[k0+q][c]) x[q][:]   for all c < k0
+        for (int c = tid; c < k0; c += CH_THREADS) {
+            cplx cq[CH_NB];
+#pragma unroll
+            for (int q = 0; q < CH_NB; ++q) cq[q] = (q < nb) ? A[(size_t)(k0 + q) * ld + c] : mk(0.0, 0.0);
+            for (int r = 0; r < nrx; ++r) {
+                cplx v = th[c * nrx + r];
+#pragma unroll
+                for (int q = 0; q < CH_NB; ++q)
+                    if (q < nb) cfmsc(v, th[(k0 + q) * nrx + r], cq[q]);  // v -= x_q conj(C[k0+q][c])
+                th[c * nrx + r] = v;
+            }
+        }
     }
+    __syncthreads();
     cplx* out = theta + (size_t)b * d.L * nrx;
     bool bad = false;
     for (int e = tid; e < d.L * nrx; e += CH_THREADS) {
@@ -388,17 +511,34 @@ __global__ void __launch_bounds__(CH_THREADS, 2) k_chol(Dims d, cplx* __restrict
     if (bad && stat) atomicOr(&stat[b], SBCE_ST_NONFINITE);
 }
 
-cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
-                              cudaStream_t s) {
-    size_t panel = (size_t)d.Ltot * CH_SP;
-    size_t thsz = (size_t)d.Lp * d.n_rx;
-    size_t smem = sizeof(cplx) * (2 * CH_NB * (CH_NB + 1) + (panel > thsz ? panel : thsz));
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int T, int MB>
+static cudaError_t run_chol(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
+                            size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(k_chol<T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_chol<<<nb, CH_THREADS, smem, s>>>(d, (cplx*)G, (cplx*)theta, active, stat);
+    k_chol<T, MB><<<nb, T, smem, s>>>(d, (cplx*)G, (cplx*)theta, active, stat);
     count_launch();
     return cudaGetLastError();
+}
+
+cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
+                              cudaStream_t s) {
+    size_t thsz = (size_t)d.Lp * d.n_rx;
+    size_t smem = sizeof(cplx) * (2 * CH_NB * CH_DS + thsz);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    // CTA shape (SBCE_CHOL_VARIANT selects alternatives for experiments)
+    static int variant = -1;
+    if (variant < 0) {
+        const char* v = getenv("SBCE_CHOL_VARIANT");
+        variant = v ? atoi(v) : 0;
+    }
+    // measured on B200 (N=64, 4x4: L=260, 592 trials): 128x4 1.40 ms, 256x2 2.0 ms, 288x1 2.9 ms -- the kernel
+    // is latency bound, more resident trials per SM win even though their factors no longer all fit in L2
+    switch (variant) {
+        case 2: return run_chol<256, 2>(d, nb, G, theta, active, stat, smem, s);
+        case 3: return run_chol<288, 1>(d, nb, G, theta, active, stat, smem, s);
+        default: return run_chol<128, 4>(d, nb, G, theta, active, stat, smem, s);
+    }
 }
 
 }  // namespace sbce

@@ -17,8 +17,8 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import (FLAG_GENIE_STOP, FLAG_PSI_SHARED, FLAG_QUIRKS, FLAG_ZERO_START, MODE_HARD, MODE_PM,
-                   MODE_PM_BETA, MODE_SOFT)
+from ._lib import (FLAG_FULL_SCAN, FLAG_GENIE_STOP, FLAG_PSI_SHARED, FLAG_QUIRKS, FLAG_ZERO_START, MODE_HARD,
+                   MODE_PM, MODE_PM_BETA, MODE_SOFT)
 
 MODES = {"soft": MODE_SOFT, "hard": MODE_HARD, "pm": MODE_PM, "pm_beta": MODE_PM_BETA}
 
@@ -40,6 +40,7 @@ class Problem:
     zero_start: bool = False
     psi_shared: bool = False
     partition_r: float = 0.0
+    full_scan: bool = False   # E-step visits every tree node instead of skipping provably weightless subtrees
 
     @property
     def L(self):
@@ -56,6 +57,7 @@ class Problem:
         flags |= FLAG_QUIRKS if self.quirks else 0
         flags |= FLAG_PSI_SHARED if self.psi_shared else 0
         flags |= FLAG_ZERO_START if self.zero_start else 0
+        flags |= FLAG_FULL_SCAN if self.full_scan else 0
         c = _lib.Cfg()
         c.N, c.n_tx, c.n_rx, c.M = self.N, self.n_tx, self.n_rx, self.M
         c.T_p, c.T_d, c.itera, c.batch = self.T_p, self.T_d, self.itera, batch

@@ -69,6 +69,42 @@ def test_estep_matches_oracle(S, orc, case, hard):
             np.testing.assert_allclose(ls[b], lo, rtol=1e-10, atol=1e-8)
 
 
+@pytest.mark.parametrize("case", [(8, 2, 2, 16, 40, 0.1), (6, 3, 3, 16, 24, 0.4), (8, 4, 4, 16, 24, 0.1),
+                                  (8, 4, 4, 16, 12, 5.0), (6, 4, 4, 4, 30, 0.2), (5, 4, 4, 64, 4, 0.3),
+                                  (5, 3, 4, 64, 6, 2.0)])
+@pytest.mark.parametrize("hard", [False, True])
+def test_subtree_skipping_is_bit_identical_to_full_scan(S, case, hard):
+    """The default E-step skips subtrees whose partial distance exceeds incumbent + 64 varn^2; such
+    nodes can neither improve the arg-min nor enter the posterior sums, so every output must be
+    bit-identical to the scan that visits all M^(n_tx-1) nodes (SBCE_FLAG_FULL_SCAN)."""
+    import torch
+
+    N, n_tx, n_rx, M, T_d, varn = case
+    B = 3
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, 4, T_d, varn, B, seed=31 + N, legacy=False)
+    rng = np.random.default_rng(3)
+    theta = tb.h + 0.1 * (rng.standard_normal(tb.h.shape) + 1j * rng.standard_normal(tb.h.shape))
+    theta[2] = 0.5 * tb.h[2]
+    outs = []
+    for full in (False, True):
+        prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=4, T_d=T_d, itera=1, mode="hard" if hard else "soft",
+                         full_scan=full)
+        ses = S.DeviceSession(prob, B)
+        dev = ses.device
+        outs.append([x.cpu().numpy() for x in ses.estep(torch.from_numpy(tb.Yd).to(dev), torch.from_numpy(tb.PsiD).to(dev),
+                                                        torch.from_numpy(theta).to(dev), torch.from_numpy(tb.varn).to(dev))])
+    (m0, R0, k0, l0), (m1, R1, k1, l1) = outs
+    assert np.array_equal(k0, k1)
+    if varn < 1.0 or hard:
+        for a, b in ((m0, m1), (R0, R1), (l0, l1)):
+            assert np.array_equal(a, b)
+    else:
+        # flat posteriors overflow the candidate queue mid-scan; the flush points (hence the summation
+        # order) may differ between the two scans, the sums agree to rounding
+        for a, b in ((m0, m1), (R0, R1), (l0, l1)):
+            np.testing.assert_allclose(a, b, rtol=1e-13, atol=1e-13)
+
+
 def test_estep_zero_theta_is_uniform_posterior(S, orc):
     """theta = 0 (first iteration of the zero-start scripts): every hypothesis ties; posterior
     uniform, arg-max = index 0 (np.argmax first-index rule)."""
