@@ -36,7 +36,102 @@ namespace sbce {
 constexpr int GR_THREADS = 256;
 constexpr int GR_TC = 16;  // symbols per shared-memory chunk
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// FP64 tensor-path MMA (SASS: 4 x DMMA.8x8x4).  Fragment layout verified by tools/microbench/dmma_layout.cu.
+__device__ __forceinline__ void dmma16x8x8(double (&c)[4], const double (&a)[4], double b0, double b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b0), "d"(b1));
+}
+
+
 constexpr int RH_MAXR = 8;
+
+// The last CTA of every trial: right-hand side rows B^H stored under the matrix,
+//   row Lp + r, column l = n*n_tx + i :  conj(B[l][r]) = sum_t psi[t,n] conj(m_t[i] y_t[r]),
+// one thread per column l with n_rx accumulators, plus the identity padding of the trapezoid.
+template <int NTX>
+__device__ __forceinline__ void gram_rhs_cta(const Dims& d, int T, int b, cplx* sPsi, cplx* sRr, const cplx* psi_b,
+                                             const cplx* __restrict__ Y, const cplx* __restrict__ sm, const cplx* Gi,
+                                             cplx* Gb) {
+    const int N1 = d.N1;
+    // ---------------- right-hand side rows + padding
+    const int n_rx = d.n_rx, L = d.L;
+    const cplx* m_b = sm + (size_t)b * T * NTX;
+    const cplx* y_b = Y + (size_t)b * T * n_rx;
+    // each thread owns columns l and l + GR_THREADS of a 2*GR_THREADS-wide pass (one pass for L <= 512)
+    for (int l0 = 0; l0 < L; l0 += 2 * GR_THREADS) {
+        int ls[2], ns[2], is[2];
+        bool have[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            ls[u] = l0 + u * GR_THREADS + threadIdx.x;
+            have[u] = ls[u] < L;
+            ns[u] = have[u] ? ls[u] / NTX : 0;
+            is[u] = have[u] ? ls[u] % NTX : 0;
+        }
+        cplx acc[2][RH_MAXR];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int r = 0; r < RH_MAXR; ++r) acc[u][r] = mk(0.0, 0.0);
+        for (int t0 = 0; t0 < T; t0 += GR_TC) {
+            const int tc = min(GR_TC, T - t0);
+            __syncthreads();
+            for (int e = threadIdx.x; e < tc * N1; e += GR_THREADS) sPsi[e] = psi_b[(size_t)t0 * N1 + e];
+            for (int e = threadIdx.x; e < tc * NTX * n_rx; e += GR_THREADS) {
+                const int tt = e / (NTX * n_rx), ii = (e / n_rx) % NTX, r = e % n_rx;
+                sRr[e] = cconj(cmul(m_b[(size_t)(t0 + tt) * NTX + ii], y_b[(size_t)(t0 + tt) * n_rx + r]));
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (have[u]) {
+                    for (int tt = 0; tt < tc; ++tt) {
+                        const cplx p = sPsi[tt * N1 + ns[u]];
+                        const cplx* z = sRr + (tt * NTX + is[u]) * n_rx;
+#pragma unroll
+                        for (int r = 0; r < RH_MAXR; ++r)
+                            if (r < n_rx) cfma(acc[u][r], p, z[r]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (have[u]) {
+#pragma unroll
+                for (int r = 0; r < RH_MAXR; ++r)
+                    if (r < n_rx) {
+                        const size_t o = (size_t)(d.Lp + r) * d.Lp + ls[u];
+                        cplx v = acc[u][r];
+                        if (Gi) v = cadd(v, Gi[o]);
+                        Gb[o] = v;
+                    }
+            }
+        }
+    }
+    // padding: identity on the padded diagonal rows L..Lp-1, zero padded columns / rows of B^H
+    const int padrows = (d.Lp - d.L) + d.RP;
+    for (int e = threadIdx.x; e < padrows * d.Lp; e += GR_THREADS) {
+        const int pr = e / d.Lp, c = e % d.Lp;
+        if (pr < d.Lp - d.L) {
+            const int row = d.L + pr;
+            Gb[(size_t)row * d.Lp + c] = (c == row) ? mk(1.0, 0.0) : mk(0.0, 0.0);
+        } else {
+            const int r = pr - (d.Lp - d.L);
+            if (r >= d.n_rx || c >= d.L) Gb[(size_t)(d.Lp + r) * d.Lp + c] = mk(0.0, 0.0);
+        }
+    }
+}
 
 // CTAs 0 .. nP-1: one thread per lower-triangular (n >= n') pair of RIS indices.
 // CTA nP (the last one of a trial): the right-hand side rows B^H stored under the matrix,
@@ -61,74 +156,7 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_gram(Dims d, int T, const cpl
     const cplx* Gi = Ginit ? Ginit + (size_t)b * gstride : nullptr;
 
     if (blockIdx.x == gridDim.x - 1) {
-        // ---------------- right-hand side rows + padding
-        const int n_rx = d.n_rx, L = d.L;
-        const cplx* m_b = sm + (size_t)b * T * NTX;
-        const cplx* y_b = Y + (size_t)b * T * n_rx;
-        // each thread owns columns l and l + GR_THREADS of a 2*GR_THREADS-wide pass (one pass for L <= 512)
-        for (int l0 = 0; l0 < L; l0 += 2 * GR_THREADS) {
-            int ls[2], ns[2], is[2];
-            bool have[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                ls[u] = l0 + u * GR_THREADS + threadIdx.x;
-                have[u] = ls[u] < L;
-                ns[u] = have[u] ? ls[u] / NTX : 0;
-                is[u] = have[u] ? ls[u] % NTX : 0;
-            }
-            cplx acc[2][RH_MAXR];
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int r = 0; r < RH_MAXR; ++r) acc[u][r] = mk(0.0, 0.0);
-            for (int t0 = 0; t0 < T; t0 += GR_TC) {
-                const int tc = min(GR_TC, T - t0);
-                __syncthreads();
-                for (int e = threadIdx.x; e < tc * N1; e += GR_THREADS) sPsi[e] = psi_b[(size_t)t0 * N1 + e];
-                for (int e = threadIdx.x; e < tc * NTX * n_rx; e += GR_THREADS) {
-                    const int tt = e / (NTX * n_rx), ii = (e / n_rx) % NTX, r = e % n_rx;
-                    sRr[e] = cconj(cmul(m_b[(size_t)(t0 + tt) * NTX + ii], y_b[(size_t)(t0 + tt) * n_rx + r]));
-                }
-                __syncthreads();
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (have[u]) {
-                        for (int tt = 0; tt < tc; ++tt) {
-                            const cplx p = sPsi[tt * N1 + ns[u]];
-                            const cplx* z = sRr + (tt * NTX + is[u]) * n_rx;
-#pragma unroll
-                            for (int r = 0; r < RH_MAXR; ++r)
-                                if (r < n_rx) cfma(acc[u][r], p, z[r]);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (have[u]) {
-#pragma unroll
-                    for (int r = 0; r < RH_MAXR; ++r)
-                        if (r < n_rx) {
-                            const size_t o = (size_t)(d.Lp + r) * d.Lp + ls[u];
-                            cplx v = acc[u][r];
-                            if (Gi) v = cadd(v, Gi[o]);
-                            Gb[o] = v;
-                        }
-                }
-            }
-        }
-        // padding: identity on the padded diagonal rows L..Lp-1, zero padded columns / rows of B^H
-        const int padrows = (d.Lp - d.L) + d.RP;
-        for (int e = threadIdx.x; e < padrows * d.Lp; e += GR_THREADS) {
-            const int pr = e / d.Lp, c = e % d.Lp;
-            if (pr < d.Lp - d.L) {
-                const int row = d.L + pr;
-                Gb[(size_t)row * d.Lp + c] = (c == row) ? mk(1.0, 0.0) : mk(0.0, 0.0);
-            } else {
-                const int r = pr - (d.Lp - d.L);
-                if (r >= d.n_rx || c >= d.L) Gb[(size_t)(d.Lp + r) * d.Lp + c] = mk(0.0, 0.0);
-            }
-        }
+        gram_rhs_cta<NTX>(d, T, b, sPsi, sRr, psi_b, Y, sm, Gi, Gb);
         return;
     }
 
@@ -148,9 +176,6 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_gram(Dims d, int T, const cpl
     // combine at the end:  acc[i][j] = (U - V, W + Z),  acc[j][i] = (U + V, Z - W).
     constexpr int NPAIR = NTX * (NTX - 1) / 2;
     constexpr int NPAIR1 = NPAIR > 0 ? NPAIR : 1;
-    constexpr int DP = (NTX + 1) & ~1;            // diagonal reals, padded to keep the complex part 16-B aligned
-    constexpr int RST = DP + 2 * NPAIR;           // doubles per symbol in the staged R chunk
-    double* sRd = (double*)sRr;                   // [GR_TC][RST]
     double dg_re[NTX], dg_im[NTX];
     double U[NPAIR1], V[NPAIR1], W[NPAIR1], Z[NPAIR1];
 #pragma unroll
@@ -159,48 +184,55 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_gram(Dims d, int T, const cpl
     for (int q = 0; q < NPAIR1; ++q) { U[q] = 0.0; V[q] = 0.0; W[q] = 0.0; Z[q] = 0.0; }
 
     const cplx* R_b = sR + (size_t)b * T * NTX * NTX;
-
-    for (int t0 = 0; t0 < T; t0 += GR_TC) {
+    // two-stage cp.async pipeline: chunk c+1 streams into the other buffer while chunk c is consumed
+    const int stage_elems = GR_TC * (N1 + NTX * NTX);      // complex elements per stage
+    auto issue = [&](int chunk, int buf) {
+        const int t0 = chunk * GR_TC;
         const int tc = min(GR_TC, T - t0);
+        cplx* dpsi = gsm + buf * stage_elems;
+        cplx* dR = dpsi + GR_TC * N1;
+        const cplx* spsi = psi_b + (size_t)t0 * N1;
+        const cplx* sRg = R_b + (size_t)t0 * NTX * NTX;
+        for (int e = threadIdx.x; e < tc * N1; e += GR_THREADS) cp_async16(dpsi + e, spsi + e);
+        for (int e = threadIdx.x; e < tc * NTX * NTX; e += GR_THREADS) cp_async16(dR + e, sRg + e);
+        cp_async_commit();
+    };
+    const int nchunk = (T + GR_TC - 1) / GR_TC;
+    if (nchunk > 0) issue(0, 0);
+    for (int ck = 0; ck < nchunk; ++ck) {
+        const int buf = ck & 1;
+        if (ck + 1 < nchunk) { issue(ck + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncthreads();
-        for (int e = threadIdx.x; e < tc * N1; e += GR_THREADS) sPsi[e] = psi_b[(size_t)t0 * N1 + e];
-        for (int e = threadIdx.x; e < tc * NTX * NTX; e += GR_THREADS) {
-            const int tt = e / (NTX * NTX), i = (e / NTX) % NTX, j = e % NTX;
-            if (j >= i) {
-                const cplx v = R_b[(size_t)t0 * NTX * NTX + e];
-                if (i == j) sRd[tt * RST + i] = v.x;
-                else {
-                    const int q = i * NTX - i * (i + 1) / 2 + (j - i - 1);  // upper-triangle pair index
-                    sRd[tt * RST + DP + 2 * q] = v.x;
-                    sRd[tt * RST + DP + 2 * q + 1] = v.y;
-                }
-            }
-        }
-        __syncthreads();
+        const int tc = min(GR_TC, T - ck * GR_TC);
+        const cplx* cPsi = gsm + buf * stage_elems;
+        const cplx* cR = cPsi + GR_TC * N1;
         if (is_pair) {
-#pragma unroll 2
+#pragma unroll 4
             for (int tt = 0; tt < tc; ++tt) {
-                const cplx a = sPsi[tt * N1 + n];
-                const cplx c = sPsi[tt * N1 + np];
+                const cplx a = cPsi[tt * N1 + n];
+                const cplx c = cPsi[tt * N1 + np];
                 const cplx p = cmulc(c, a);  // conj(psi[t,n]) psi[t,n']
-                const double* Rt = sRd + tt * RST;
+                const cplx* Rt = cR + tt * NTX * NTX;
 #pragma unroll
                 for (int i = 0; i < NTX; ++i) {
-                    const double r = Rt[i];
+                    const double r = Rt[i * NTX + i].x;
                     dg_re[i] = fma(p.x, r, dg_re[i]);
                     dg_im[i] = fma(p.y, r, dg_im[i]);
                 }
-                const cplx* Ru = (const cplx*)(Rt + DP);
 #pragma unroll
-                for (int q = 0; q < NPAIR; ++q) {
-                    const cplx r = Ru[q];
-                    U[q] = fma(p.x, r.x, U[q]);
-                    V[q] = fma(p.y, r.y, V[q]);
-                    W[q] = fma(p.x, r.y, W[q]);
-                    Z[q] = fma(p.y, r.x, Z[q]);
-                }
+                for (int i = 0; i < NTX; ++i)
+#pragma unroll
+                    for (int j = i + 1; j < NTX; ++j) {
+                        const int q = i * NTX - i * (i + 1) / 2 + (j - i - 1);
+                        const cplx r = Rt[i * NTX + j];
+                        U[q] = fma(p.x, r.x, U[q]);
+                        V[q] = fma(p.y, r.y, V[q]);
+                        W[q] = fma(p.x, r.y, W[q]);
+                        Z[q] = fma(p.y, r.x, Z[q]);
+                    }
             }
         }
+        __syncthreads();  // everyone is done with this buffer before it is refilled (chunk ck+2)
     }
     if (is_pair) {
         auto put = [&](int i, int j, cplx v) {
@@ -221,6 +253,145 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_gram(Dims d, int T, const cpl
     }
 }
 
+// ---------------------------------------------------------------------------
+// Gram on the FP64 tensor path, n_tx = 4.
+// With the Hermitian product sharing above, the 32 real accumulators of a RIS pair are
+//   [pr ; pi] (2 x T)  times  Bmat (T x 16 real columns = [Rd0..Rd3, (Rr,Ri) of the 6 upper entries]),
+// i.e. the whole Gram is ONE real GEMM with M = 2 x (number of pairs), N = 16, K = T whose A operand
+// p_t = conj(psi[t,n]) psi[t,n'] is generated on the fly into the mma.m16n8k8 fragment layout from the
+// staged psi chunk.  A warp owns two 16-pair tiles; per 8 symbols it issues 8 MMAs (= 32 DMMA.8x8x4)
+// against 20 shared-memory loads, so the kernel is bound by the FP64 pipe, not by shared memory.
+// B-matrix column -> double offset inside the raw 4x4 complex R_t (row-major, interleaved):
+__device__ __forceinline__ int gram_bcol_offset(int col) {
+    // cols 0..3: real diagonal (i,i) ; cols 4+2q, 5+2q: re, im of the q-th upper entry (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
+    const int up[6] = {1, 2, 3, 6, 7, 11};  // 4*i + j
+    if (col < 4) return 2 * (5 * col);
+    const int q = (col - 4) >> 1;
+    return 2 * up[q] + ((col - 4) & 1);
+}
+
+__global__ void __launch_bounds__(GR_THREADS, 2) k_gram_mma4(Dims d, int T, const cplx* __restrict__ Psi,
+                                                           const cplx* __restrict__ sR, const cplx* __restrict__ Y,
+                                                           const cplx* __restrict__ sm, const cplx* __restrict__ Ginit,
+                                                           cplx* __restrict__ Gout, const int32_t* __restrict__ active) {
+    constexpr int NTX = 4;
+    extern __shared__ double2 gsm[];
+    const int b = blockIdx.y;
+    if (active != nullptr && active[b] == 0) return;
+    const int N1 = d.N1;
+    const int P = N1 * (N1 + 1) / 2;
+    const cplx* psi_b = Psi + (size_t)(d.psi_shared ? 0 : b) * T * N1;
+    const size_t gstride = (size_t)d.Ltot * d.Lp;
+    cplx* Gb = Gout + (size_t)b * gstride;
+    const cplx* Gi = Ginit ? Ginit + (size_t)b * gstride : nullptr;
+    if (blockIdx.x == gridDim.x - 1) {
+        gram_rhs_cta<NTX>(d, T, b, gsm, gsm + GR_TC * N1, psi_b, Y, sm, Gi, Gb);
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    // pairs of this lane: tile u (0,1), row half h (0,1) -> item
+    int pn[2][2], pnp[2][2];
+    bool pv[2][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int item = blockIdx.x * GR_THREADS + (2 * warp + u) * 16 + g + 8 * h;
+            pv[u][h] = item < P;
+            item = min(item, P - 1);
+            int n = (int)((sqrt(8.0 * item + 1.0) - 1.0) * 0.5);
+            while ((n + 1) * (n + 2) / 2 <= item) ++n;
+            while (n * (n + 1) / 2 > item) --n;
+            pn[u][h] = n;
+            pnp[u][h] = item - n * (n + 1) / 2;
+        }
+    const int boff0 = gram_bcol_offset(g), boff1 = gram_bcol_offset(8 + g);
+    double accr[2][2][4], acci[2][2][4];  // [tile][n-tile][c0..c3]
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { accr[u][nt][e] = 0.0; acci[u][nt][e] = 0.0; }
+
+    const cplx* R_b = sR + (size_t)b * T * NTX * NTX;
+    const int stage_elems = GR_TC * (N1 + NTX * NTX);
+    auto issue = [&](int chunk, int buf) {
+        const int t0 = chunk * GR_TC;
+        const int tc = min(GR_TC, T - t0);
+        cplx* dpsi = gsm + buf * stage_elems;
+        cplx* dR = dpsi + GR_TC * N1;
+        const cplx* spsi = psi_b + (size_t)t0 * N1;
+        const cplx* sRg = R_b + (size_t)t0 * NTX * NTX;
+        for (int e = threadIdx.x; e < tc * N1; e += GR_THREADS) cp_async16(dpsi + e, spsi + e);
+        for (int e = threadIdx.x; e < tc * NTX * NTX; e += GR_THREADS) cp_async16(dR + e, sRg + e);
+        if (tc < GR_TC) {  // ragged last chunk: symbols beyond T contribute zero
+            for (int e = tc * N1 + threadIdx.x; e < GR_TC * N1; e += GR_THREADS) dpsi[e] = mk(0.0, 0.0);
+            for (int e = tc * NTX * NTX + threadIdx.x; e < GR_TC * NTX * NTX; e += GR_THREADS) dR[e] = mk(0.0, 0.0);
+        }
+        cp_async_commit();
+    };
+    const int nchunk = (T + GR_TC - 1) / GR_TC;
+    if (nchunk > 0) issue(0, 0);
+    for (int ck = 0; ck < nchunk; ++ck) {
+        const int buf = ck & 1;
+        if (ck + 1 < nchunk) { issue(ck + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        const cplx* cPsi = gsm + buf * stage_elems;
+        const double* cR = (const double*)(cPsi + GR_TC * N1);
+#pragma unroll
+        for (int ks = 0; ks < GR_TC / 8; ++ks) {
+            const int tlo = ks * 8 + tig, thi = tlo + 4;
+            const double b00 = cR[tlo * 32 + boff0], b01 = cR[thi * 32 + boff0];
+            const double b10 = cR[tlo * 32 + boff1], b11 = cR[thi * 32 + boff1];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                // A fragment order: (row g, t lo), (row g+8, t lo), (row g, t hi), (row g+8, t hi)
+                const cplx p0 = cmulc(cPsi[tlo * N1 + pnp[u][0]], cPsi[tlo * N1 + pn[u][0]]);
+                const cplx p1 = cmulc(cPsi[tlo * N1 + pnp[u][1]], cPsi[tlo * N1 + pn[u][1]]);
+                const cplx p2 = cmulc(cPsi[thi * N1 + pnp[u][0]], cPsi[thi * N1 + pn[u][0]]);
+                const cplx p3 = cmulc(cPsi[thi * N1 + pnp[u][1]], cPsi[thi * N1 + pn[u][1]]);
+                const double pr[4] = {p0.x, p1.x, p2.x, p3.x};
+                const double pi[4] = {p0.y, p1.y, p2.y, p3.y};
+                dmma16x8x8(accr[u][0], pr, b00, b01);
+                dmma16x8x8(accr[u][1], pr, b10, b11);
+                dmma16x8x8(acci[u][0], pi, b00, b01);
+                dmma16x8x8(acci[u][1], pi, b10, b11);
+            }
+        }
+        __syncthreads();
+    }
+    // epilogue: accumulator (row g + 8h, cols 2 tig, 2 tig + 1 of n-tile nt)
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (!pv[u][h]) continue;
+            const int n = pn[u][h], np = pnp[u][h];
+            auto put = [&](int i, int j, cplx v) {
+                const size_t o = (size_t)(n * NTX + i) * d.Lp + (np * NTX + j);
+                if (Gi) v = cadd(v, Gi[o]);
+                Gb[o] = v;
+            };
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const double r0 = accr[u][nt][2 * h], r1 = accr[u][nt][2 * h + 1];
+                const double i0 = acci[u][nt][2 * h], i1 = acci[u][nt][2 * h + 1];
+                const int col = 8 * nt + 2 * tig;
+                if (col < 4) {  // two diagonal entries: (pr Rd, pi Rd)
+                    put(col, col, mk(r0, i0));
+                    put(col + 1, col + 1, mk(r1, i1));
+                } else {        // one upper pair q: U = pr Rr, W = pr Ri, Z = pi Rr, V = pi Ri
+                    const int q = (col - 4) >> 1;
+                    const int qi = (q < 3) ? 0 : (q < 5 ? 1 : 2);
+                    const int qj = (q < 3) ? q + 1 : (q < 5 ? q - 1 : 3);
+                    put(qi, qj, mk(r0 - i1, r1 + i0));
+                    put(qj, qi, mk(r0 + i1, i0 - r1));
+                }
+            }
+        }
+}
+
 template <int NTX>
 static cudaError_t run_gram(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Y,
                             const double* sm, const double* Ginit, double* Gout, const int32_t* active,
@@ -228,13 +399,29 @@ static cudaError_t run_gram(const Dims& d, int nb, const double* Psi, int T, con
     const int P = d.N1 * (d.N1 + 1) / 2;
     dim3 grid((P + GR_THREADS - 1) / GR_THREADS + 1, nb);   // + 1: the right-hand-side / padding CTA
     const int zsz = NTX * (d.n_rx > NTX ? d.n_rx : NTX);
-    size_t smem = sizeof(cplx) * (size_t)(GR_TC * d.N1 + GR_TC * zsz);
+    size_t smem = sizeof(cplx) * (size_t)(2 * GR_TC * (d.N1 + NTX * NTX));          // two cp.async stages (pair CTAs)
+    const size_t smem_rhs = sizeof(cplx) * (size_t)(GR_TC * d.N1 + GR_TC * zsz);     // rhs CTA, single stage
+    if (smem_rhs > smem) smem = smem_rhs;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_gram<NTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_gram<NTX><<<grid, GR_THREADS, smem, s>>>(d, T, (const cplx*)Psi, (const cplx*)sR, (const cplx*)Y,
-                                               (const cplx*)sm, (const cplx*)Ginit, (cplx*)Gout, active);
+    static int use_mma = -1;
+    if (use_mma < 0) {
+        const char* v = getenv("SBCE_GRAM_SCALAR");
+        use_mma = (v && atoi(v)) ? 0 : 1;
+    }
+    if (NTX == 4 && use_mma) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_gram_mma4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        k_gram_mma4<<<grid, GR_THREADS, smem, s>>>(d, T, (const cplx*)Psi, (const cplx*)sR, (const cplx*)Y,
+                                                   (const cplx*)sm, (const cplx*)Ginit, (cplx*)Gout, active);
+    } else {
+        k_gram<NTX><<<grid, GR_THREADS, smem, s>>>(d, T, (const cplx*)Psi, (const cplx*)sR, (const cplx*)Y,
+                                                   (const cplx*)sm, (const cplx*)Ginit, (cplx*)Gout, active);
+    }
     count_launch();
     return cudaGetLastError();
 }
@@ -259,12 +446,6 @@ cudaError_t launch_normal_equations(const Dims& d, int nb, const double* Psi, in
 constexpr int CH_NB = 16;            // panel width
 constexpr int CH_DS = CH_NB + 1;     // row stride (complex) of the shared 16x16 blocks
 
-__device__ __forceinline__ void dmma16x8x8(double (&c)[4], const double (&a)[4], double b0, double b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
-        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b0), "d"(b1));
-}
 
 // LEFT-looking blocked complex Cholesky on the FP64 tensor path (mma.sync m16n8k8.f64, SASS DMMA).
 // Per 16-column panel k, three phases separated by CTA barriers:
