@@ -49,11 +49,14 @@ extern "C" {
 #define SBCE_MODE_HARD 1    /* arg-max hypothesis, rank-one statistics (em_ml / log-max)  */
 #define SBCE_MODE_PM 2      /* partitioned, candidate weight 1 (Proposed method/PM.py)    */
 #define SBCE_MODE_PM_BETA 3 /* partitioned, posterior over candidates (PM_beta.py)        */
+#define SBCE_MODE_ZF 4      /* zero-forcing detector EM (em_zf, PMvsMLvsZFvsMMSE.py:95)   */
+#define SBCE_MODE_MMSE 5    /* MMSE detector EM (em_mmse, PMvsMLvsZFvsMMSE.py:54)         */
 
 /* flags */
 #define SBCE_FLAG_GENIE_STOP 1u /* stop a trial when | ||theta|| - ||h_true|| | < 1 and l != 0 (PM.py:110)   */
-#define SBCE_FLAG_QUIRKS 2u     /* PM modes: reproduce the off-by-one psi slice (PM.py:63) and the un-permuted
-                                   candidate vector (PM.py:102); cleared = corrected behaviour             */
+#define SBCE_FLAG_QUIRKS 2u     /* PM / ZF / MMSE modes: reproduce the off-by-one psi slice (PM.py:63), the
+                                   un-permuted candidate vector (PM.py:102) and the table-indexing slicer
+                                   nearest_symbol_ecul (PMvsMLvsZFvsMMSE.py:49-52); cleared = corrected behaviour */
 #define SBCE_FLAG_PSI_SHARED 4u /* PsiP / PsiD are shared by all trials of the batch ([T][N+1], no batch dim) */
 #define SBCE_FLAG_ZERO_START 8u /* theta0 is ignored, EM starts from 0 (Proposed_method_NMSEvsTp.py:45)      */
 #define SBCE_FLAG_FULL_SCAN 16u /* E-step visits every node of the hypothesis tree.  Default (flag clear): subtrees

@@ -455,3 +455,81 @@ def em_pm(Yd, Yp, PsiD, PsiP, Xp, M, varn, itera, theta0, h_true=None, partition
         if genie_stop and h_true is not None and l != 0 and abs(np.linalg.norm(Theta) - np.linalg.norm(h_true)) < 1:
             break
     return (Theta, dict(iters=iters)) if return_trace else Theta
+
+
+# --------------------------------------------------------------------------
+# detector-driven EM (zero forcing / MMSE), SURVEY section 8f-3
+# --------------------------------------------------------------------------
+
+def slicer_as_coded(data_est, cons, n_tx):
+    """`Proposed method/PMvsMLvsZFvsMMSE.py:49-52` (nearest_symbol_ecul) as it is CALLED
+    (:68,:109): `estimated_symbol` is (n_tx,1), `constellation` is the (K,n_tx) hypothesis table, so
+    `estimated_symbol - s` broadcasts to (n_tx,n_tx) and np.argmin runs over the flattened
+    (K,n_tx,n_tx) array of |data_est[i] - s_k[j]|; the flat index is then used as a ROW index into the
+    table (quirk).  Closed form of that flat index: let (i*, c*) minimise
+    |data_est[i] - c| over streams and constellation points (first i on ties, first c on ties); the
+    first table row containing c* is k = idx(c*), where it sits in the last stream (or in stream 0
+    when idx = 0), hence flat = idx * n_tx^2 + i* * n_tx + (n_tx-1 if idx else 0)."""
+    M = len(cons)
+    dist = np.abs(data_est.reshape(-1, 1) - cons.reshape(1, -1))      # (n_tx, M)
+    vmin = dist.min()
+    # first (k,i,j) in flat order attaining vmin: smallest idx first, then smallest i
+    cand = [(int(c), int(i)) for i in range(n_tx) for c in range(M) if dist[i, c] == vmin]
+    idx, i_star = min(cand)
+    flat = idx * n_tx * n_tx + i_star * n_tx + ((n_tx - 1) if idx else 0)
+    if flat >= M ** n_tx:
+        raise IndexError("reference slicer indexes past the hypothesis table")
+    return hypothesis_digits(np.array(flat), M, n_tx)
+
+
+def detector_stats(Yd, PsiD, Theta, cons, n_tx, varn, kind, quirks=True):
+    """Per-symbol rank-one statistics of `em_zf` / `em_mmse`
+    (`Proposed method/PMvsMLvsZFvsMMSE.py:54-133`): effective channel with the off-by-one psi slice
+    (:64,:105, quirk Q4), x = pinv(H) y (ZF, :66) or inv(H^H H + varn^2 I) H^H y (MMSE, :107), then the
+    slicer above (quirks) or a proper per-stream nearest-point slicer (quirks off)."""
+    T_d, N1 = PsiD.shape
+    N = N1 - 1
+    n_rx = Yd.shape[1]
+    M = len(cons)
+    Th = Theta.reshape(N1, n_tx, n_rx)
+    Heff = effective_channels(PsiD, Theta, n_tx)
+    m = np.zeros((T_d, n_tx), dtype=np.complex128)
+    R = np.zeros((T_d, n_tx, n_tx), dtype=np.complex128)
+    for t in range(T_d):
+        if quirks:
+            chan = Th[0].T + np.einsum("n,njr->rj", PsiD[t, :N], Th[1:])
+        else:
+            chan = Heff[t]
+        if kind == "zf":
+            est = np.linalg.pinv(chan) @ Yd[t]
+        else:
+            est = np.linalg.inv(chan.conj().T @ chan + (varn ** 2) * np.eye(n_tx)) @ chan.conj().T @ Yd[t]
+        if quirks:
+            dig = slicer_as_coded(est, cons, n_tx)
+        else:
+            dig = np.array([int(np.argmin(np.abs(est[j] - cons) ** 2)) for j in range(n_tx)])
+        x = cons[dig]
+        m[t] = x.conj()
+        R[t] = x.conj()[:, None] * x[None, :]
+    return m, R
+
+
+def em_detector(Yd, Yp, PsiD, PsiP, Xp, M, varn, itera, theta0, kind="zf", h_true=None, genie_stop=True,
+                quirks=True, return_trace=False):
+    """`em_zf` (`PMvsMLvsZFvsMMSE.py:95-133`) / `em_mmse` (:54-93).  NOTE the genie stop of em_zf has no
+    `l != 0` guard (:128) while em_mmse's has (:87)."""
+    n_tx = Xp.shape[1]
+    cons = qam_constellation(M)
+    Theta = np.array(theta0, dtype=np.complex128)
+    mp_, Rp_ = pilot_stats(Xp)
+    Gp, Bp = gram_and_rhs(PsiP, Yp, mp_, Rp_)
+    iters = 0
+    for l in range(itera):
+        m, R = detector_stats(Yd, PsiD, Theta, cons, n_tx, varn, kind, quirks)
+        Gd, Bd = gram_and_rhs(PsiD, Yd, m, R)
+        Theta = solve_normal(Gp + Gd, Bp + Bd)
+        iters = l + 1
+        if genie_stop and h_true is not None and (l != 0 or kind == "zf") \
+                and abs(np.linalg.norm(Theta) - np.linalg.norm(h_true)) < 1:
+            break
+    return (Theta, dict(iters=iters)) if return_trace else Theta

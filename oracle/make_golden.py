@@ -209,6 +209,32 @@ def case_multi(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn, partition_r)
     _save(name, meta, d)
 
 
+def case_detectors(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn):
+    """em_zf / em_mmse only (`Proposed method/PMvsMLvsZFvsMMSE.py:54-133`), genie stop active."""
+    ns = rh.load_functions("Proposed method/PMvsMLvsZFvsMMSE.py", N=N, n_tx=n_tx, n_rx=n_rx, beta_max=TWO_PI)
+    np.random.seed(seed)
+    out = {}
+    with rh.quiet():
+        h = ns["channelMatrix"](n_tx, n_rx, N, 1)
+        X_d, aps, qamCons = ns["symbols"](n_tx, M, T_d)
+        X_p = ns["pilotSymbols"](n_tx, M, T_p)
+        ns["h"] = h
+        PsiTilde_tp, PsiTilde_td = ns["irsMatrix"](T_p, T_d, N, 0, 1)
+        PsiTilde_td = np.insert(PsiTilde_td, 0, np.ones((1, T_d), dtype="complex128"), axis=0)
+        Y_p, Y_d, Z_p, Z_d, h_initial = ns["receivedSignals"](T_p, T_d, PsiTilde_tp, PsiTilde_td, n_rx, n_tx, X_d, X_p, h, varn, M)
+        ns["Z_d"] = Z_d
+        out["theta_zf"] = ns["em_zf"](Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, aps, M, varn, itera, h_initial, h)
+        out["theta_mmse"] = ns["em_mmse"](Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, aps, M, varn, itera, h_initial, h)
+    g = dict(h=h, X_d=X_d, X_p=X_p, PsiTilde_tp=PsiTilde_tp, PsiTilde_td=PsiTilde_td, Y_p=Y_p, Y_d=Y_d, Z_p=Z_p, h_initial=h_initial)
+    d = _dense(g, n_tx, n_rx)
+    L = (N + 1) * n_tx
+    meta = dict(kind="detectors", order="multi", variant="pm", seed=seed, N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d,
+                itera=itera, varn=varn, src="Proposed method/PMvsMLvsZFvsMMSE.py:em_zf,em_mmse")
+    for k, v in out.items():
+        d[k + "_ref"] = np.asarray(v, dtype=np.complex128).reshape(L, n_rx)
+    _save(name, meta, d)
+
+
 def case_script(name, relpath, seed):
     """A whole top-level script, unmodified, after np.random.seed(seed)."""
     t0 = time.time()
@@ -253,6 +279,12 @@ def main(argv):
         case_pm("pm_beta_3x3_s13", 13, 4, 3, 3, 4, 24, 16, 3, 0.5, 2, True)
     if want("multi_s3"):
         case_multi("multi_s3", 3, 8, 2, 2, 4, 12, 40, 3, 0.1, 1)
+    if want("det_16qam_s31"):
+        case_detectors("det_16qam_s31", 31, 6, 2, 2, 16, 6, 24, 4, 0.3)
+    if want("det_3x3_s32"):
+        case_detectors("det_3x3_s32", 32, 5, 3, 3, 4, 5, 20, 4, 0.5)
+    if want("det_2x4_s33"):
+        case_detectors("det_2x4_s33", 33, 7, 2, 4, 4, 7, 30, 5, 1.0)
     if want("script_top_td_s0"):
         case_script("script_top_td_s0", "Proposed_method_NMSEvsTd.py", 0)
     if want("script_top_tp_s0"):

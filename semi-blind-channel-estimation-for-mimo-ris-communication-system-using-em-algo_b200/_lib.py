@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsbce.so")
 
-MODE_SOFT, MODE_HARD, MODE_PM, MODE_PM_BETA = 0, 1, 2, 3
+MODE_SOFT, MODE_HARD, MODE_PM, MODE_PM_BETA, MODE_ZF, MODE_MMSE = 0, 1, 2, 3, 4, 5
 FLAG_GENIE_STOP, FLAG_QUIRKS, FLAG_PSI_SHARED, FLAG_ZERO_START, FLAG_FULL_SCAN = 1, 2, 4, 8, 16
 ST_NOT_PD, ST_NONFINITE = 1, 2
 

@@ -47,7 +47,7 @@ static int make_dims(const sbce_cfg* c, Dims* d) {
     if (c->M == 4) sq = 2; else if (c->M == 16) sq = 4; else if (c->M == 64) sq = 8; else return SBCE_E_UNSUPPORTED;
     if (c->n_tx > 4) return SBCE_E_UNSUPPORTED;
     if (!(c->n_rx <= 4 || c->n_rx == 6 || c->n_rx == 8)) return SBCE_E_UNSUPPORTED;
-    if (c->mode < SBCE_MODE_SOFT || c->mode > SBCE_MODE_PM_BETA) return SBCE_E_UNSUPPORTED;
+    if (c->mode < SBCE_MODE_SOFT || c->mode > SBCE_MODE_MMSE) return SBCE_E_UNSUPPORTED;
     d->N = c->N; d->N1 = c->N + 1; d->n_tx = c->n_tx; d->n_rx = c->n_rx; d->M = c->M; d->sqM = sq;
     d->bitsM = (sq == 2 ? 2 : (sq == 4 ? 4 : 6));
     d->T_p = c->T_p; d->T_d = c->T_d; d->itera = c->itera;
@@ -58,10 +58,10 @@ static int make_dims(const sbce_cfg* c, Dims* d) {
     d->mode = c->mode; d->flags = c->flags; d->p1 = c->partition_p1;
     d->psi_shared = (c->flags & SBCE_FLAG_PSI_SHARED) ? 1 : 0;
     d->rec = qr_record_doubles(c->n_tx);
-    if (c->mode >= SBCE_MODE_PM) {
+    if (c->mode == SBCE_MODE_PM || c->mode == SBCE_MODE_PM_BETA) {
         if (c->partition_p1 < 1 || c->partition_p1 > c->n_tx) return SBCE_E_SHAPE;
-        if (c->n_rx < c->n_tx) return SBCE_E_UNSUPPORTED;
     }
+    if (c->mode >= SBCE_MODE_PM && c->n_rx < c->n_tx) return SBCE_E_UNSUPPORTED;
     return 0;
 }
 
@@ -96,7 +96,7 @@ size_t carve_workspace(const Dims& d, int nb, void* base, Workspace* ws) {
 // forward declaration (pm.cu)
 cudaError_t launch_pm_stats(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
                             const double* varn, const int32_t* active, double* stat_m, double* stat_R,
-                            cudaStream_t s);
+                            int32_t* kstar, cudaStream_t s);
 
 static int estep_dispatch(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
                           const double* varn, const int32_t* active, Workspace& ws, double* stat_m, double* stat_R,
@@ -112,7 +112,7 @@ static int estep_dispatch(const Dims& d, int nb, const double* Yd, const double*
         }
     } else {
         PhaseScope ps(SBCE_PHASE_ENUM, s);
-        CK(launch_pm_stats(d, nb, Yd, PsiD, theta, varn, active, stat_m, stat_R, s));
+        CK(launch_pm_stats(d, nb, Yd, PsiD, theta, varn, active, stat_m, stat_R, kstar, s));
     }
     return 0;
 }
@@ -361,14 +361,21 @@ namespace {
 struct DevPool {
     void* p = nullptr;
     size_t cap = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // compute + device->host
+    cudaStream_t copy = nullptr;     // host->device, runs ahead of the compute stream
+    cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 std::mutex g_mu;
 DevPool g_pool[16];
 
 int pool_get(int dev, size_t bytes, DevPool** out) {
     DevPool& P = g_pool[dev];
-    if (!P.stream) CK(cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking));
+    if (!P.stream) {
+        CK(cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&P.copy, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&P.ev[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&P.ev[1], cudaEventDisableTiming));
+    }
     if (P.cap < bytes) {
         if (P.p) CK(cudaFree(P.p));
         P.p = nullptr;
@@ -432,9 +439,6 @@ int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device) {
     if (rc) return rc;
     char* base = (char*)P->p;
     cudaStream_t s = P->stream;
-    Seg* ins[] = {&sYd, &sYp, &sPd, &sPp, &sXp, &sT0, &sVn, &sHt, &sXd};
-    for (Seg* q : ins)
-        if (q->h && q->bytes) CK(cudaMemcpyAsync(base + q->off, q->h, q->bytes, cudaMemcpyHostToDevice, s));
     sbce_io dio;
     memset(&dio, 0, sizeof(dio));
     auto dp = [&](const Seg& q) { return (q.h || q.hout) ? (double*)(base + q.off) : nullptr; };
@@ -442,12 +446,49 @@ int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device) {
     dio.theta0 = dp(sT0); dio.varn = dp(sVn); dio.h_true = dp(sHt); dio.Xd_true = dp(sXd);
     dio.theta = dp(oTh); dio.kstar = (int32_t*)dp(oKs); dio.llf = dp(oLl); dio.lse = dp(oLs); dio.nmse = dp(oNm);
     dio.iters = (int32_t*)dp(oIt); dio.status = (int32_t*)dp(oSt);
-    rc = sbce_em_batch(cfg, &dio, base + al(io_bytes), ws_bytes, (void*)s);
-    if (rc) return rc;
-    Seg* outs[] = {&oTh, &oKs, &oLl, &oLs, &oNm, &oIt, &oSt};
-    for (Seg* q : outs)
-        if (q->hout && q->bytes) CK(cudaMemcpyAsync(q->hout, base + q->off, q->bytes, cudaMemcpyDeviceToHost, s));
+
+    // Large batches go in two halves: the host->device copy of the second half overlaps the kernels of
+    // the first (copy stream runs ahead; the compute stream waits on one event per half).  Below ~1200
+    // trials the kernels lose more from the smaller launch than the overlap wins (measured on B200).
+    const int nhalf = (cfg->batch >= 1184) ? 2 : 1;
+    const int half = (cfg->batch + nhalf - 1) / nhalf;
+    struct Part { Seg* q; size_t per_trial; };
+    Part ins[] = {{&sYd, (size_t)d.T_d * d.n_rx * 16}, {&sYp, (size_t)d.T_p * d.n_rx * 16},
+                  {&sPd, d.psi_shared ? 0 : (size_t)d.T_d * d.N1 * 16}, {&sPp, d.psi_shared ? 0 : (size_t)d.T_p * d.N1 * 16},
+                  {&sXp, (size_t)d.T_p * d.n_tx * 16}, {&sT0, Ln}, {&sVn, 8}, {&sHt, Ln},
+                  {&sXd, (size_t)d.T_d * d.n_tx * 16}};
+    Part outs[] = {{&oTh, Ln}, {&oKs, (size_t)d.T_d * 4}, {&oLl, (size_t)d.itera * 8}, {&oLs, (size_t)d.itera * 8},
+                   {&oNm, 8}, {&oIt, 4}, {&oSt, 4}};
+    for (int hf = 0; hf < nhalf; ++hf) {
+        const size_t b0 = (size_t)hf * half;
+        const size_t nb = (b0 + half <= B) ? (size_t)half : B - b0;
+        for (Part& pt : ins) {
+            if (!pt.q->h || !pt.q->bytes) continue;
+            if (pt.per_trial == 0) {  // shared across the batch: once
+                if (hf == 0) CK(cudaMemcpyAsync(base + pt.q->off, pt.q->h, pt.q->bytes, cudaMemcpyHostToDevice, P->copy));
+            } else {
+                CK(cudaMemcpyAsync(base + pt.q->off + b0 * pt.per_trial, (const char*)pt.q->h + b0 * pt.per_trial,
+                                   nb * pt.per_trial, cudaMemcpyHostToDevice, P->copy));
+            }
+        }
+        CK(cudaEventRecord(P->ev[hf], P->copy));
+    }
+    for (int hf = 0; hf < nhalf; ++hf) {
+        const size_t b0 = (size_t)hf * half;
+        const size_t nb = (b0 + half <= B) ? (size_t)half : B - b0;
+        CK(cudaStreamWaitEvent(s, P->ev[hf], 0));
+        sbce_cfg c2 = *cfg;
+        c2.batch = (int32_t)nb;
+        sbce_io o = offset_io(d, dio, b0);
+        rc = sbce_em_batch(&c2, &o, base + al(io_bytes), ws_bytes, (void*)s);
+        if (rc) return rc;
+        for (Part& pt : outs)
+            if (pt.q->hout && pt.q->bytes)
+                CK(cudaMemcpyAsync((char*)pt.q->hout + b0 * pt.per_trial, base + pt.q->off + b0 * pt.per_trial,
+                                   nb * pt.per_trial, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(P->copy));
     return 0;
 }
 

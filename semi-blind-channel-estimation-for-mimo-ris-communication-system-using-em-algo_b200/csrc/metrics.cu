@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(256) k_after_iteration(Dims d, int l, const cp
         }
         a = block_sum(a, red);
         c = block_sum(c, red);
-        if (threadIdx.x == 0 && l != 0 && fabs(sqrt(a) - sqrt(c)) < 1.0) active[b] = 0;
+        // em_zf's stop has no `l != 0` guard (PMvsMLvsZFvsMMSE.py:128); every other estimator's has
+        const bool guard_ok = (l != 0) || (d.mode == SBCE_MODE_ZF);
+        if (threadIdx.x == 0 && guard_ok && fabs(sqrt(a) - sqrt(c)) < 1.0) active[b] = 0;
     }
 }
 

@@ -270,6 +270,7 @@ __device__ __forceinline__ int gram_bcol_offset(int col) {
     return 2 * up[q] + ((col - 4) & 1);
 }
 
+constexpr int GM_TC = 32;  // symbols per stage of the tensor-path Gram
 __global__ void __launch_bounds__(GR_THREADS, 2) k_gram_mma4(Dims d, int T, const cplx* __restrict__ Psi,
                                                            const cplx* __restrict__ sR, const cplx* __restrict__ Y,
                                                            const cplx* __restrict__ sm, const cplx* __restrict__ Ginit,
@@ -315,32 +316,32 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_gram_mma4(Dims d, int T, cons
             for (int e = 0; e < 4; ++e) { accr[u][nt][e] = 0.0; acci[u][nt][e] = 0.0; }
 
     const cplx* R_b = sR + (size_t)b * T * NTX * NTX;
-    const int stage_elems = GR_TC * (N1 + NTX * NTX);
+    const int stage_elems = GM_TC * (N1 + NTX * NTX);
     auto issue = [&](int chunk, int buf) {
-        const int t0 = chunk * GR_TC;
-        const int tc = min(GR_TC, T - t0);
+        const int t0 = chunk * GM_TC;
+        const int tc = min(GM_TC, T - t0);
         cplx* dpsi = gsm + buf * stage_elems;
-        cplx* dR = dpsi + GR_TC * N1;
+        cplx* dR = dpsi + GM_TC * N1;
         const cplx* spsi = psi_b + (size_t)t0 * N1;
         const cplx* sRg = R_b + (size_t)t0 * NTX * NTX;
         for (int e = threadIdx.x; e < tc * N1; e += GR_THREADS) cp_async16(dpsi + e, spsi + e);
         for (int e = threadIdx.x; e < tc * NTX * NTX; e += GR_THREADS) cp_async16(dR + e, sRg + e);
-        if (tc < GR_TC) {  // ragged last chunk: symbols beyond T contribute zero
-            for (int e = tc * N1 + threadIdx.x; e < GR_TC * N1; e += GR_THREADS) dpsi[e] = mk(0.0, 0.0);
-            for (int e = tc * NTX * NTX + threadIdx.x; e < GR_TC * NTX * NTX; e += GR_THREADS) dR[e] = mk(0.0, 0.0);
+        if (tc < GM_TC) {  // ragged last chunk: symbols beyond T contribute zero
+            for (int e = tc * N1 + threadIdx.x; e < GM_TC * N1; e += GR_THREADS) dpsi[e] = mk(0.0, 0.0);
+            for (int e = tc * NTX * NTX + threadIdx.x; e < GM_TC * NTX * NTX; e += GR_THREADS) dR[e] = mk(0.0, 0.0);
         }
         cp_async_commit();
     };
-    const int nchunk = (T + GR_TC - 1) / GR_TC;
+    const int nchunk = (T + GM_TC - 1) / GM_TC;
     if (nchunk > 0) issue(0, 0);
     for (int ck = 0; ck < nchunk; ++ck) {
         const int buf = ck & 1;
         if (ck + 1 < nchunk) { issue(ck + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncthreads();
         const cplx* cPsi = gsm + buf * stage_elems;
-        const double* cR = (const double*)(cPsi + GR_TC * N1);
+        const double* cR = (const double*)(cPsi + GM_TC * N1);
 #pragma unroll
-        for (int ks = 0; ks < GR_TC / 8; ++ks) {
+        for (int ks = 0; ks < GM_TC / 8; ++ks) {
             const int tlo = ks * 8 + tig, thi = tlo + 4;
             const double b00 = cR[tlo * 32 + boff0], b01 = cR[thi * 32 + boff0];
             const double b10 = cR[tlo * 32 + boff1], b11 = cR[thi * 32 + boff1];
@@ -412,6 +413,8 @@ static cudaError_t run_gram(const Dims& d, int nb, const double* Psi, int T, con
         use_mma = (v && atoi(v)) ? 0 : 1;
     }
     if (NTX == 4 && use_mma) {
+        const size_t smem_mma = sizeof(cplx) * (size_t)(2 * GM_TC * (d.N1 + NTX * NTX));
+        if (smem_mma > smem) smem = smem_mma;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(k_gram_mma4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;

@@ -84,7 +84,7 @@ __device__ int slice_qam(cplx z, int sqM, int hb) {
 __global__ void __launch_bounds__(128) k_pm_stats(Dims d, const cplx* __restrict__ Yd, const cplx* __restrict__ PsiD,
                                                   const cplx* __restrict__ theta, const double* __restrict__ varn,
                                                   const int32_t* __restrict__ active, cplx* __restrict__ stat_m,
-                                                  cplx* __restrict__ stat_R) {
+                                                  cplx* __restrict__ stat_R, int32_t* __restrict__ kstar) {
     const int b = blockIdx.y;
     if (active != nullptr && active[b] == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -120,6 +120,69 @@ __global__ void __launch_bounds__(128) k_pm_stats(Dims d, const cplx* __restrict
 
     cplx y[PM_MAXR];
     for (int r = 0; r < n_rx; ++r) y[r] = Yd[((size_t)b * d.T_d + t) * n_rx + r];
+
+    if (d.mode == SBCE_MODE_ZF || d.mode == SBCE_MODE_MMSE) {
+        // ---- detector-driven EM (em_zf / em_mmse, PMvsMLvsZFvsMMSE.py:54-133): x = (H^H H [+ varn^2 I])^-1 H^H y,
+        // sliced to one hypothesis, rank-one statistics.  Every lane computes the same tiny solve.
+        cplx Gm[PM_MAXT][PM_MAXT], est[PM_MAXT];
+        const double reg = (d.mode == SBCE_MODE_MMSE) ? varn[b] * varn[b] : 0.0;
+        for (int a = 0; a < n_tx; ++a)
+            for (int c = 0; c <= a; ++c) {
+                cplx sacc = mk(0, 0);
+                for (int r = 0; r < n_rx; ++r) cfmac(sacc, Hc[r][c], Hc[r][a]);
+                if (a == c) sacc.x += reg;
+                Gm[a][c] = sacc;
+            }
+        small_chol(Gm, n_tx);
+        for (int a = 0; a < n_tx; ++a) {
+            cplx sacc = mk(0, 0);
+            for (int r = 0; r < n_rx; ++r) cfmac(sacc, y[r], Hc[r][a]);
+            est[a] = sacc;
+        }
+        for (int a = 0; a < n_tx; ++a) {
+            cplx v = est[a];
+            for (int q = 0; q < a; ++q) { cplx nv = cmul(Gm[a][q], est[q]); v = csub(v, nv); }
+            est[a] = cscale(v, 1.0 / Gm[a][a].x);
+        }
+        for (int a = n_tx - 1; a >= 0; --a) {
+            cplx v = est[a];
+            for (int q = a + 1; q < n_tx; ++q) cfmsc(v, est[q], Gm[q][a]);
+            est[a] = cscale(v, 1.0 / Gm[a][a].x);
+        }
+        int k = 0;
+        if (quirks) {
+            // nearest_symbol_ecul as called (PMvsMLvsZFvsMMSE.py:49-52,68): argmin over the flattened
+            // (K, n_tx, n_tx) array of |est[i] - table[k][j]| used as a ROW index of the table.  With (i*, c*)
+            // the closest (stream, constellation point) pair, first c then first i on ties, that flat index is
+            // idx(c*) n_tx^2 + i* n_tx + (n_tx-1 if idx(c*) else 0).
+            double best = 1e300;
+            int bi = 0, bc = 0;
+            for (int c = 0; c < M; ++c) {
+                const cplx cv = cons_val(c, sqM, hb);
+                for (int i = 0; i < n_tx; ++i) {
+                    const double dd = cnorm2(csub(est[i], cv));
+                    if (dd < best) { best = dd; bc = c; bi = i; }
+                }
+            }
+            k = bc * n_tx * n_tx + bi * n_tx + (bc ? n_tx - 1 : 0);
+            int K = 1;
+            for (int a = 0; a < n_tx; ++a) K *= M;
+            if (k >= K) k = K - 1;  // the reference would raise IndexError here (only when n_tx^2 > M^(n_tx-1))
+        } else {
+            for (int a = 0; a < n_tx; ++a) k = k * M + slice_qam(est[a], sqM, hb);
+        }
+        if (lane == 0) {
+            const size_t sidx = (size_t)b * d.T_d + t;
+            cplx X[PM_MAXT];
+            for (int a = n_tx - 1, kk = k; a >= 0; --a) { X[a] = cons_val(kk % M, sqM, hb); kk /= M; }
+            for (int i = 0; i < n_tx; ++i) {
+                stat_m[sidx * n_tx + i] = cconj(X[i]);
+                for (int j = 0; j < n_tx; ++j) stat_R[(sidx * n_tx + i) * n_tx + j] = cmulc(X[j], X[i]);
+            }
+            if (kstar) kstar[sidx] = k;
+        }
+        return;
+    }
 
     // ---- ordering (PM.py:65-70)
     int order[PM_MAXT], remaining[PM_MAXT];
@@ -262,11 +325,11 @@ __global__ void __launch_bounds__(128) k_pm_stats(Dims d, const cplx* __restrict
 
 cudaError_t launch_pm_stats(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
                             const double* varn, const int32_t* active, double* stat_m, double* stat_R,
-                            cudaStream_t s) {
+                            int32_t* kstar, cudaStream_t s) {
     if (d.n_tx > PM_MAXT || d.n_rx > PM_MAXR) return cudaErrorInvalidValue;
     dim3 grid((d.T_d + 3) / 4, nb);
     k_pm_stats<<<grid, 128, 0, s>>>(d, (const cplx*)Yd, (const cplx*)PsiD, (const cplx*)theta, varn, active,
-                                    (cplx*)stat_m, (cplx*)stat_R);
+                                    (cplx*)stat_m, (cplx*)stat_R, kstar);
     count_launch();
     return cudaGetLastError();
 }

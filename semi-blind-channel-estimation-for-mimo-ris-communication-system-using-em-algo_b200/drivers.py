@@ -34,7 +34,7 @@ class SweepConfig:
     itera: int = 5
     monte_iter: int = 16
     varn: float = 0.1
-    mode: str = "soft"            # soft | hard | pm | pm_beta
+    mode: str = "soft"            # soft | hard | pm | pm_beta | zf | mmse
     start: str = "ls"             # ls (h_initial, PM.py:147) | zero (Proposed_method_NMSEvsTp.py:45)
     genie_stop: bool = False
     quirks: bool = True
@@ -152,7 +152,7 @@ def nmse_vs_snr(cfg: SweepConfig, snr_db: Sequence[float], runner=None, device=0
     return _sweep(cfg, snr_db, lambda c, x: replace(c, varn=float(snr_to_varn(x))), runner, device, keep_per_trial)
 
 
-def detectors_vs_snr(cfg: SweepConfig, snr_db: Sequence[float], modes=("pm_beta", "hard", "soft"), runner=None,
+def detectors_vs_snr(cfg: SweepConfig, snr_db: Sequence[float], modes=("pm_beta", "hard", "zf", "mmse", "soft"), runner=None,
                      device=0):
     """One NMSE-vs-SNR curve per estimator on identically seeded data (all_Detectors.py:356-395)."""
     out = {}

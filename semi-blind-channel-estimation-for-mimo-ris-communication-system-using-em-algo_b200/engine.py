@@ -18,9 +18,10 @@ import numpy as np
 
 from . import _lib
 from ._lib import (FLAG_FULL_SCAN, FLAG_GENIE_STOP, FLAG_PSI_SHARED, FLAG_QUIRKS, FLAG_ZERO_START, MODE_HARD,
-                   MODE_PM, MODE_PM_BETA, MODE_SOFT)
+                   MODE_MMSE, MODE_PM, MODE_PM_BETA, MODE_SOFT, MODE_ZF)
 
-MODES = {"soft": MODE_SOFT, "hard": MODE_HARD, "pm": MODE_PM, "pm_beta": MODE_PM_BETA}
+MODES = {"soft": MODE_SOFT, "hard": MODE_HARD, "pm": MODE_PM, "pm_beta": MODE_PM_BETA, "zf": MODE_ZF,
+         "mmse": MODE_MMSE}
 
 
 @dataclass

@@ -11,6 +11,7 @@ became keyword arguments or are inferred from the arrays.
   em_ser    /root/reference/Proposed method/SER/log_max_SER.py:51 (hard decisions, returns X_dest)
   em_pm     /root/reference/Proposed method/PM.py:47 (partitioned, weight 1, lstsq)
   em_pm_beta /root/reference/Proposed method/PM_beta.py:42 (partitioned, posterior weights)
+  em_zf, em_mmse /root/reference/Proposed method/PMvsMLvsZFvsMMSE.py:95,54 (detector-driven EM)
 """
 from __future__ import annotations
 
@@ -159,6 +160,27 @@ def em_pm_beta(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, M, varn, itera, h_initial, 
     """Partitioned EM with posterior-weighted candidates (PM_beta.py:42-112)."""
     res, _ = _run("pm_beta", Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, M, varn, itera, h_initial, n_tx, cons=qamCons,
                   h=h, genie_stop=genie_stop, partition_r=partition_r, quirks=quirks, **kw)
+    return res.theta.reshape(-1, 1)
+
+
+def em_zf(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, all_possibleSymbols, M, varn, itera, h_initial, h, *,
+          genie_stop=True, quirks=True, **kw):
+    """Zero-forcing detector EM (PMvsMLvsZFvsMMSE.py:95-133).  quirks=True reproduces the off-by-one psi slice,
+    the table-indexing slicer and the genie stop without the `l != 0` guard."""
+    n_tx = _ntx_from_table(all_possibleSymbols)
+    cons = constellation_from_table(all_possibleSymbols, M)
+    res, _ = _run("zf", Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, M, varn, itera, h_initial, n_tx, cons=cons, h=h,
+                  genie_stop=genie_stop, quirks=quirks, **kw)
+    return res.theta.reshape(-1, 1)
+
+
+def em_mmse(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, all_possibleSymbols, M, varn, itera, h_initial, h, *,
+            genie_stop=True, quirks=True, **kw):
+    """MMSE detector EM (PMvsMLvsZFvsMMSE.py:54-93)."""
+    n_tx = _ntx_from_table(all_possibleSymbols)
+    cons = constellation_from_table(all_possibleSymbols, M)
+    res, _ = _run("mmse", Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, M, varn, itera, h_initial, n_tx, cons=cons, h=h,
+                  genie_stop=genie_stop, quirks=quirks, **kw)
     return res.theta.reshape(-1, 1)
 
 

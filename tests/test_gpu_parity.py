@@ -358,6 +358,38 @@ def test_em_pm_batch_matches_oracle(S, orc, case):
         assert relerr(res.theta[b], ref) < 1e-8, (b, relerr(res.theta[b], ref))
 
 
+@pytest.mark.parametrize("name", golden_names(["multi", "detectors"]))
+def test_em_zf_mmse_golden(S, orc, name):
+    """em_zf / em_mmse against the literal PMvsMLvsZFvsMMSE.py (genie stop active, all quirks on)."""
+    meta, g = load_golden(name)
+    n_tx, n_rx, M = int(meta["n_tx"]), int(meta["n_rx"]), int(meta["M"])
+    T_d, T_p, varn, itera = int(meta["T_d"]), int(meta["T_p"]), float(meta["varn"]), int(meta["itera"])
+    Y_d, Y_p, Z_p, PsiTilde_td = _ref_objects(g, n_rx)
+    table = orc.hypothesis_table(orc.qam_constellation(M), n_tx)
+    h0 = g["theta0"].reshape(-1, 1)
+    th = S.em_zf(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, table, M, varn, itera, h0, g["h"].reshape(-1))
+    assert relerr(th.reshape(g["h"].shape), g["theta_zf_ref"]) < RTOL
+    th = S.em_mmse(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, table, M, varn, itera, h0, g["h"].reshape(-1))
+    assert relerr(th.reshape(g["h"].shape), g["theta_mmse_ref"]) < RTOL
+
+
+@pytest.mark.parametrize("case", [(8, 2, 2, 4, 8, 30, 3, 0.3, "zf", True), (8, 2, 2, 4, 8, 30, 3, 0.3, "mmse", True),
+                                  (8, 3, 3, 4, 8, 30, 3, 0.5, "zf", False), (6, 4, 4, 16, 6, 40, 2, 0.5, "mmse", False),
+                                  (6, 2, 4, 16, 6, 30, 3, 1.0, "zf", True), (6, 3, 4, 4, 6, 30, 3, 2.0, "mmse", True)])
+def test_em_detector_batch_matches_oracle(S, orc, case):
+    N, n_tx, n_rx, M, T_p, T_d, itera, varn, mode, quirks = case
+    B = 4
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn, B, seed=91, legacy=False)
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera, mode=mode, quirks=quirks,
+                     genie_stop=True)
+    res = S.run_host(prob, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, tb.varn, theta0=tb.theta0, h_true=tb.h)
+    for b in range(B):
+        ref, tr = orc.em_detector(tb.Yd[b], tb.Yp[b], tb.PsiD[b], tb.PsiP[b], tb.Xp[b], M, varn, itera, tb.theta0[b],
+                                  kind=mode, h_true=tb.h[b], genie_stop=True, quirks=quirks, return_trace=True)
+        assert int(res.iters[b]) == tr["iters"]
+        assert relerr(res.theta[b], ref) < RTOL
+
+
 def test_genie_stop_iteration_counts(S, orc):
     N, n_tx, n_rx, M, T_p, T_d, itera, varn = 8, 2, 2, 4, 8, 40, 6, 0.1
     B = 6

@@ -29,7 +29,7 @@ def _regen(meta):
     return orc.gen_trial(seed=None, rs=rs, order=order, variant=str(meta["variant"]), **kw)
 
 
-@pytest.mark.parametrize("name", golden_names(["soft", "hard", "pm", "pm_beta", "multi"]))
+@pytest.mark.parametrize("name", golden_names(["soft", "hard", "pm", "pm_beta", "multi", "detectors"]))
 def test_generator_is_byte_identical(name):
     meta, g = load_golden(name)
     if str(meta.get("h_order", "F")) == "C":
@@ -172,3 +172,16 @@ def test_script_top_tp_unmodified_wellposed_points():
             assert abs(orc.nmse(th, h) - ref[i]) <= 5e-5 * ref[i], (T_p, orc.nmse(th, h), ref[i])
             checked += 1
     assert checked >= 2
+
+
+@pytest.mark.parametrize("name", golden_names(["multi", "detectors"]))
+def test_zf_mmse_detector_em_matches_reference(name):
+    """em_zf / em_mmse of PMvsMLvsZFvsMMSE.py including the slicer that indexes the hypothesis table
+    with a flattened (K,n_tx,n_tx) argmin."""
+    meta, g = load_golden(name)
+    M, varn, itera = int(meta["M"]), float(meta["varn"]), int(meta["itera"])
+    args = (g["Yd"], g["Yp"], g["PsiD"], g["PsiP"], g["Xp"], M, varn, itera, g["theta0"])
+    th = orc.em_detector(*args, kind="zf", h_true=g["h"])
+    assert relerr(th, g["theta_zf_ref"]) < RTOL_THETA
+    th = orc.em_detector(*args, kind="mmse", h_true=g["h"])
+    assert relerr(th, g["theta_mmse_ref"]) < RTOL_THETA
