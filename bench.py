@@ -49,23 +49,37 @@ def workload_name(w):
 # ---------------------------------------------------------------------------
 
 def flops_models(w):
+    """Per trial-iteration flop counts (add = mul = 1, FMA = 2); stated in DESIGN.md section 5.
+    `*_survey` entries are SURVEY.md section 8d's algorithmic figures; the un-suffixed ones count what the
+    kernels of this repository execute (used for roofline fractions, so that a cheaper algorithm does
+    not read as a higher utilisation)."""
     N1, n_tx, n_rx, M, T_d = w["N"] + 1, w["n_tx"], w["n_rx"], w["M"], w["T_d"]
     L = N1 * n_tx
+    P = N1 * (N1 + 1) // 2
     sq = int(round(M ** 0.5))
-    # hypothesis tree: level s (stream s fixed) costs 5 + 2 s flops per node at that level, every
-    # deepest node pays the separable leaf scan (3 sqrt(M) + 2 flops)
-    enum, count = 0.0, 1.0
-    for s in range(n_tx - 1, 0, -1):
-        count *= M
-        enum += count * (5 + 2 * s)
-    enum += count * (3 * sq + 2)
+    import math
+    lg = int(math.log2(sq // 2)) if sq >= 2 else 0
+    # hypothesis tree, FULL scan: every deepest node (M^(n_tx-1) of them) costs the separable update of the
+    # row-0 residual (2 FMA), its partial distance (1 add), two folds (1+log2(sqrt(M)/2) subtractions each),
+    # the leaf minimum (2 FMA) and one compare; each group of M deepest nodes shares 4 sqrt(M) flops of
+    # separable level-1 distances; prefix levels cost ~6+2s flops per node above.
+    nodes = float(M) ** (n_tx - 1)
+    f_node = 4 + 1 + 2 * (1 + lg) + 4 + 1
+    enum = nodes * f_node
+    if n_tx >= 2:
+        enum += (nodes / M) * 4 * sq
+    cnt = 1.0
+    for s in range(n_tx - 1, 1, -1):
+        cnt *= M
+        enum += cnt * (6 + 2 * s)
     nr = max(n_rx, n_tx)
+    gram_exec = (64.0 + 8.0) * P * T_d if n_tx == 4 else (2.0 * (2 * n_tx + 4 * n_tx * (n_tx - 1) // 2 * 2) + 8.0) * P * T_d
     return dict(
-        enum=T_d * enum,                                               # per trial-iteration
+        enum_full_scan=T_d * enum,
         heff_qr=T_d * (8.0 * N1 * n_tx * n_rx + 16.0 * n_tx * n_tx * nr),
-        gram=4.0 * T_d * L * (L + 1),                                  # SURVEY 8d F_G
-        chol=4.0 * L ** 3 / 3.0 + 8.0 * n_rx * L * L,                  # SURVEY 8d F_S
-        rhs=8.0 * T_d * L * (n_rx + 1),                                # SURVEY 8d F_B
+        gram=gram_exec + 8.0 * T_d * L * n_rx,          # Hermitian-shared real GEMM + p_t generation + rhs rows
+        gram_survey=4.0 * T_d * L * (L + 1) + 8.0 * T_d * L * (n_rx + 1),   # SURVEY 8d F_G + F_B
+        chol=4.0 * L ** 3 / 3.0 + 8.0 * n_rx * L * L,   # SURVEY 8d F_S (complex Cholesky + two triangular solves)
         survey_estep=T_d * (float(M) ** n_tx * (2 * n_tx * n_rx + 4 * n_rx + 3 + 4 * n_tx + 2 * n_tx * (n_tx + 1))
                             + 8.0 * N1 * n_tx * n_rx + 8.0 * n_tx * M * n_rx),  # SURVEY 8d F_E (naive enumeration)
     )
@@ -324,6 +338,8 @@ def run_ours(args):
         if name in fm:
             k["tflops"] = fm[name] * B / avg_s / 1e12
             k["frac_fp64_peak"] = k["tflops"] / fp64_peak if fp64_peak > 0 else None
+        if name + "_survey" in fm:
+            k["tflops_survey_model"] = fm[name + "_survey"] * B / avg_s / 1e12
         if name in bm:
             k["gbs"] = bm[name] * B / avg_s / 1e9
             k["frac_hbm_peak"] = k["gbs"] / hbm_peak
@@ -338,7 +354,13 @@ def run_ours(args):
         roofline["hbm_side"] = dict(kernel="heff_qr", achieved=kernels["heff_qr"]["gbs"], peak=hbm_peak, unit="GB/s",
                                     frac=kernels["heff_qr"]["frac_hbm_peak"], peak_source=hbm_src)
     if "enum" in kernels:
-        roofline["estep_survey_model_tflops"] = fm["survey_estep"] * B / (kernels["enum"]["avg_launch_ms"] * 1e-3) / 1e12
+        kernels["enum"]["note"] = ("default E-step skips provably weightless subtrees: executed work is data "
+                                   "dependent, see full_scan.enum_* for the fixed-work variant")
+    if full is not None:
+        es = full["enum_avg_launch_ms"] * 1e-3
+        full["enum_tflops"] = fm["enum_full_scan"] * B / es / 1e12
+        full["enum_frac_fp64_peak"] = full["enum_tflops"] / fp64_peak if fp64_peak > 0 else None
+        full["enum_survey_model_tflops"] = fm["survey_estep"] * B / es / 1e12
 
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
     cpu = None

@@ -700,8 +700,18 @@ static cudaError_t run_chol(const Dims& d, int nb, double* G, double* theta, con
                             size_t smem, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(k_chol<T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_chol<T, MB><<<nb, T, smem, s>>>(d, (cplx*)G, (cplx*)theta, active, stat);
-    count_launch();
+    static int wave = -1;
+    if (wave < 0) {
+        const char* v = getenv("SBCE_CHOL_WAVE");
+        wave = v ? atoi(v) : 0;
+    }
+    const int step = wave > 0 ? wave : nb;
+    for (int b0 = 0; b0 < nb; b0 += step) {
+        const int n = (nb - b0 < step) ? nb - b0 : step;
+        k_chol<T, MB><<<n, T, smem, s>>>(d, (cplx*)G + (size_t)b0 * d.Ltot * d.Lp, (cplx*)theta + (size_t)b0 * d.L * d.n_rx,
+                                         active ? active + b0 : nullptr, stat ? stat + b0 : nullptr);
+        count_launch();
+    }
     return cudaGetLastError();
 }
 
@@ -721,6 +731,8 @@ cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, c
     switch (variant) {
         case 2: return run_chol<256, 2>(d, nb, G, theta, active, stat, smem, s);
         case 3: return run_chol<288, 1>(d, nb, G, theta, active, stat, smem, s);
+        case 4: return run_chol<64, 8>(d, nb, G, theta, active, stat, smem, s);
+        case 5: return run_chol<96, 5>(d, nb, G, theta, active, stat, smem, s);
         default: return run_chol<128, 4>(d, nb, G, theta, active, stat, smem, s);
     }
 }

@@ -279,3 +279,32 @@ class DesignRow:
         if isinstance(key, tuple) and len(key) == 2 and key[0] == 0 and key[1] == slice(0, None, self.n_rx):
             return self.w
         return self.dense()[key]
+
+
+# ---------------------------------------------------------------------------
+# structured-product helpers the reference keeps as dense matrices
+# ---------------------------------------------------------------------------
+
+def khatri_rao(a, b):
+    """Column-wise Kronecker product (Proposed_method_NMSEvsTd.py:9-19 / scipy.linalg.khatri_rao):
+    c[i*b.shape[0] + k, j] = a[i, j] * b[k, j]."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if a.ndim != 2 or b.ndim != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError("khatri_rao needs two 2-D arrays with the same number of columns")
+    return (a[:, None, :] * b[None, :, :]).reshape(a.shape[0] * b.shape[0], a.shape[1])
+
+
+def commutation_permutation(m, n):
+    """Index form of the commutation matrix K(m,n) of `Proposed method/commutation_matrix.py:3-8`:
+    K = I[w, :] with w = arange(m*n).reshape((m, n), order='F').T.ravel(order='F'), so that
+    K @ vec_F(A) = vec_F(A^T) for an (m, n) matrix A.  Only the permutation is returned (the reference's
+    module-level demo materialises a 65536^2 identity, 34 GB); apply it with x[w]."""
+    return np.arange(m * n).reshape((m, n), order="F").T.ravel(order="F")
+
+
+def design_index(n_prime, j, r, n_tx, n_rx):
+    """Column of the reference's Kronecker design matrix Z = psi~^T (x) x^T (x) I_nrx that multiplies
+    Theta[n'*n_tx + j, r]: (n' * n_tx + j) * n_rx + r.  This index map is all the CUDA kernels keep of
+    the Kronecker / Khatri-Rao / commutation structure."""
+    return (n_prime * n_tx + j) * n_rx + r

@@ -403,6 +403,44 @@ def test_genie_stop_iteration_counts(S, orc):
         assert relerr(res.theta[b], ref) < RTOL
 
 
+def test_shared_phase_design_across_batch(S, orc):
+    """Deterministic DFT data phases of Proposed_method_NMSEvsTd.py:92-94 are the same for every trial:
+    with SBCE_FLAG_PSI_SHARED the phase matrices are passed once ([T][N+1]) and must give the same result
+    as the per-trial layout."""
+    N, n_tx, n_rx, M, T_p, T_d, itera, varn = 12, 2, 4, 4, 16, 40, 5, 0.2
+    B = 5
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn, B, seed=4, legacy=False, variant="top_td")
+    assert np.array_equal(tb.PsiD[0], tb.PsiD[B - 1]) and np.array_equal(tb.PsiP[0], tb.PsiP[B - 1])
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera, zero_start=True)
+    full = S.run_host(prob, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, tb.varn, h_true=tb.h)
+    import dataclasses
+
+    prob_s = dataclasses.replace(prob, psi_shared=True)
+    shared = S.run_host(prob_s, tb.Yd, tb.Yp, tb.PsiD[0].copy(), tb.PsiP[0].copy(), tb.Xp, tb.varn, h_true=tb.h)
+    assert np.array_equal(full.theta, shared.theta) and np.array_equal(full.kstar, shared.kstar)
+    ref = orc.em(tb.Yd[1], tb.Yp[1], tb.PsiD[1], tb.PsiP[1], tb.Xp[1], M, varn, itera, theta0=None)
+    assert relerr(shared.theta[1], ref) < RTOL
+
+
+def test_drivers_on_gpu_match_oracle_runner(S, orc):
+    """The sweep drivers through the CUDA library equal the same drivers fed by the oracle."""
+    import sys, os
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_multirank_gloo import oracle_runner
+
+    cfg = S.SweepConfig(N=8, n_tx=2, n_rx=2, M=4, T_p=8, T_d=32, itera=3, monte_iter=6, varn=0.2, mode="hard", seed=3,
+                        max_batch=4)
+    a = S.nmse_vs_td(cfg, [32, 40])
+    b = S.nmse_vs_td(cfg, [32, 40], runner=oracle_runner)
+    np.testing.assert_allclose(a["nmse"], b["nmse"], rtol=5e-5)      # 4 significant figures
+    np.testing.assert_allclose(a["ser"], b["ser"], rtol=0, atol=0)   # decisions bit-exact -> identical SER
+    np.testing.assert_allclose(a["ser_as_coded"], b["ser_as_coded"], rtol=0, atol=0)
+    c = S.detectors_vs_snr(S.SweepConfig(N=8, n_tx=2, n_rx=2, M=4, T_p=8, T_d=24, itera=2, monte_iter=4, seed=1,
+                                         partition_r=1), [0.0, 10.0])
+    assert set(c) == {"pm_beta", "hard", "zf", "mmse", "soft"} and all(np.isfinite(v["nmse"]).all() for v in c.values())
+
+
 def test_north_star_size_properties(S):
     """N=64, 4x4, 16-QAM (K=65536): too slow for the oracle at full size, so check
     size-independent properties: (a) noiseless data with theta0 = truth is a fixed point of the

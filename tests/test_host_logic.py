@@ -143,3 +143,27 @@ def test_metrics_helpers():
     assert sbce.ser_as_coded(X_d, X_hat) == 0.5
     assert sbce.ser_true(X_d, X_hat) == 0.0
     assert sbce.ser_as_coded(X_d, X_hat) == orc.ser_as_coded(np.hstack(X_d).T, np.vstack(X_hat))
+
+
+def test_structured_product_helpers():
+    from scipy import linalg
+
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((3, 5)) + 1j * rng.standard_normal((3, 5))
+    b = rng.standard_normal((4, 5)) + 1j * rng.standard_normal((4, 5))
+    assert np.array_equal(sbce.signal_model.khatri_rao(a, b), linalg.khatri_rao(a, b))
+    m, n = 3, 4
+    A = rng.standard_normal((m, n))
+    w = sbce.signal_model.commutation_permutation(m, n)
+    K = np.eye(m * n)[w, :]                       # what commutation_matrix.py:3-8 builds densely
+    assert np.array_equal(K @ A.flatten(order="F"), A.T.flatten(order="F"))
+    assert np.array_equal(A.flatten(order="F")[w], A.T.flatten(order="F"))
+    # the index map reproduces the dense Kronecker design row
+    n_tx, n_rx, N1 = 2, 3, 4
+    psi = rng.standard_normal(N1) + 1j * rng.standard_normal(N1)
+    x = rng.standard_normal(n_tx) + 1j * rng.standard_normal(n_tx)
+    Z = np.kron(np.kron(psi[None, :], x[None, :]), np.eye(n_rx))
+    for npr in range(N1):
+        for j in range(n_tx):
+            for r in range(n_rx):
+                assert np.isclose(Z[r, sbce.signal_model.design_index(npr, j, r, n_tx, n_rx)], psi[npr] * x[j], rtol=1e-15, atol=0)
