@@ -192,7 +192,8 @@ struct EnumT {
     static constexpr int O_S2 = O_AREF + 1;     // inv_s2
     static constexpr int O_CNT = O_S2 + 1;      // int counter lives in this double slot
     static constexpr int O_Q = O_CNT + 1;       // ENUM_QCAP ints = ENUM_QCAP/2 doubles
-    static constexpr int WS_DOUBLES = ((O_Q + ENUM_QCAP / 2) + 1) & ~1;
+    static constexpr int O_SCR = O_Q + ENUM_QCAP / 2;   // [NACC][32] reduction scratch of the flush
+    static constexpr int WS_DOUBLES = ((O_SCR + NACC * 32) + 1) & ~1;
 
     __device__ __forceinline__ static double pam(int a) { return (double)(2 * a - SQM + 1); }
     __device__ __forceinline__ static cplx cval(int m) { return mk(pam(m & (SQM - 1)), pam(m >> HB)); }
@@ -247,13 +248,16 @@ __device__ __noinline__ void enum_flush(double* ws, double warp_best) {
     // one queue entry per lane per round; the warp reduces every statistic right away (rare path: keep
     // the register footprint small so that it does not limit the occupancy of the scan loop)
     double* A = ws + E::O_ACC;
-    auto radd = [&](int idx, double v) {
-        v = warp_sum(v);
-        if (lane == 0) A[idx] += v;
-    };
+    // per round every lane drops the NACC contributions of its queue entry into a shared scratch
+    // [NACC][32]; afterwards lane i sums statistic i over the lanes that held an entry (a transpose
+    // instead of NACC butterfly reductions: ~25 stores + nround loads per lane, no shuffles)
+    double* scr = ws + E::O_SCR;
+    int nround = 0;
+    auto radd = [&](int idx, double v) { scr[idx * 32 + lane] = v; };
     for (int e0 = 0; e0 < n; e0 += 32) {
         const int e = e0 + lane;
         const bool have = e < n;
+        nround = min(32, n - e0);
         const int code = have ? q[e] : 0;
         cplx t0;
         double base = ws[E::O_C0];
@@ -315,6 +319,13 @@ __device__ __noinline__ void enum_flush(double* ws, double warp_best) {
                     radd(1 + 3 * NTX + 2 * E::pair(i, s) + 1, E0 * cx.y);
                 }
         }
+        __syncwarp();
+        if (lane < E::NACC) {
+            double acc = 0.0;
+            for (int e2 = 0; e2 < nround; ++e2) acc += scr[lane * 32 + e2];
+            A[lane] += acc;
+        }
+        __syncwarp();
     }
     __syncwarp();
     if (lane == 0) {
@@ -459,7 +470,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_enum(Dims d, const double* __
                                                      double* __restrict__ lse_sym) {
     typedef EnumT<NTX, SQM> E;
     constexpr int M = E::M;
-    __shared__ __align__(16) double smem[WARPS][E::WS_DOUBLES];
+    extern __shared__ __align__(16) double enum_smem[];   // [WARPS][E::WS_DOUBLES]
     const int b = blockIdx.y;
     if (active != nullptr && active[b] == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -467,7 +478,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_enum(Dims d, const double* __
     if (t >= d.T_d) return;
 
     const double* rec = qr + ((size_t)b * d.T_d + t) * d.rec;
-    double* ws = smem[warp];
+    double* ws = enum_smem + (size_t)warp * E::WS_DOUBLES;
     cplx* tab = (cplx*)(ws + E::O_TAB);
     double* g = ws + E::O_G;
     cplx yt[NTX];
@@ -647,12 +658,23 @@ static cudaError_t run_enum(const Dims& d, int nb, const double* qr, const doubl
                             double* stat_m, double* stat_R, int32_t* kstar, double* lse_sym, cudaStream_t s) {
     constexpr int WARPS = 4;
     dim3 grid((d.T_d + WARPS - 1) / WARPS, nb);
-    if (d.mode == SBCE_MODE_HARD)
-        k_enum<NTX, SQM, true, WARPS><<<grid, WARPS * 32, 0, s>>>(d, qr, varn, active, (cplx*)stat_m, (cplx*)stat_R,
-                                                                   kstar, lse_sym);
-    else
-        k_enum<NTX, SQM, false, WARPS><<<grid, WARPS * 32, 0, s>>>(d, qr, varn, active, (cplx*)stat_m, (cplx*)stat_R,
-                                                                    kstar, lse_sym);
+    constexpr size_t smem = sizeof(double) * WARPS * EnumT<NTX, SQM>::WS_DOUBLES;
+    cudaError_t e;
+    if (d.mode == SBCE_MODE_HARD) {
+        if (smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(k_enum<NTX, SQM, true, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        k_enum<NTX, SQM, true, WARPS><<<grid, WARPS * 32, smem, s>>>(d, qr, varn, active, (cplx*)stat_m,
+                                                                      (cplx*)stat_R, kstar, lse_sym);
+    } else {
+        if (smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(k_enum<NTX, SQM, false, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        k_enum<NTX, SQM, false, WARPS><<<grid, WARPS * 32, smem, s>>>(d, qr, varn, active, (cplx*)stat_m,
+                                                                       (cplx*)stat_R, kstar, lse_sym);
+    }
     count_launch();
     return cudaGetLastError();
 }
