@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(128) k_heff_qr(Dims d, const cplx* __restrict_
         for (int j = 0; j < NTX; ++j) A[r][j] = mk(0.0, 0.0);
 
     // Heff[r][j] = sum_n' psi~[t][n'] Theta[n'*n_tx + j][r]; theta reads are warp-uniform (broadcast)
+#pragma unroll 4
     for (int n = 0; n < d.N1; ++n) {
         const cplx p = psi[n];
         const cplx* row = th + (size_t)n * NTX * NRX;
