@@ -479,17 +479,20 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol(Dims d, cplx* __re
     cplx* sD = csm;                   // [16][17] diagonal block factor (later: reduction scratch)
     cplx* sW = sD + CH_NB * CH_DS;    // [16][17] its inverse
     cplx* th = sW + CH_NB * CH_DS;    // [Lp][n_rx] solution during the back substitution
-    __shared__ int s_bad;
-    if (tid == 0) s_bad = 0;
+    __shared__ int s_bad, s_next1, s_next3;
+    if (tid == 0) { s_bad = 0; s_next1 = 1; s_next3 = 0; }
 
     for (int k0 = 0; k0 < Lp; k0 += CH_NB) {
         const int nb = min(CH_NB, Lp - k0);   // multiple of 4
         const int rows = Ltot - k0;           // rows of the panel including its diagonal block
         const int nrt = (rows + 15) >> 4;
-        __syncthreads();                      // previous panel fully written
-        // ---- phase 1: S = A - C_prev C_rows^H for every 16-row tile
-        if (k0 > 0) {
-            for (int rt = warp; rt < nrt; rt += CH_WARPS) {
+        __syncthreads();                      // previous panel fully written; tile counters reset
+        if (tid == 0) s_next3 = 0;            // phase-3 counter: idle between this barrier and the next one
+        // ---- phase 1: S = A - C_prev C_rows^H for every 16-row tile.  Tile 0 (the diagonal block) belongs to
+        // warp 0, which then goes straight on to phase 2 while the other warps keep claiming tiles from a shared
+        // counter (warp 0 joins them afterwards): the serial factorisation overlaps the panel update.
+        auto phase1_tile = [&](int rt) {
+            {
                 const int r0 = rt << 4;
                 double cr[2][4], ci[2][4];
 #pragma unroll
@@ -532,10 +535,21 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol(Dims d, cplx* __re
                         }
                     }
             }
-            __syncthreads();
+        };
+        auto claim = [&](int* counter) {
+            int v = 0;
+            if (lane == 0) v = atomicAdd(counter, 1);
+            return __shfl_sync(0xffffffffu, v, 0);
+        };
+        if (warp == 0) {
+            if (k0 > 0) phase1_tile(0);
+            __syncwarp();
+        } else if (k0 > 0) {
+            for (int rt = claim(&s_next1); rt < nrt; rt = claim(&s_next1)) phase1_tile(rt);
         }
         // ---- phase 2: diagonal block -> sD, unblocked Cholesky by warp 0 (lane = row), W = D^-1
         if (warp == 0) {
+            __threadfence_block();
             const int r = lane;
             for (int c = 0; c < CH_NB; ++c)
                 if (r < CH_NB) sD[r * CH_DS + c] = (r < nb && c <= r && c < nb) ? A[(size_t)(k0 + r) * ld + k0 + c] : mk(0.0, 0.0);
@@ -587,13 +601,17 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol(Dims d, cplx* __re
                 if (c <= rr) A[(size_t)(k0 + rr) * ld + k0 + c] = sD[rr * CH_DS + c];
             }
         }
+        if (warp == 0 && k0 > 0) {
+            for (int rt = claim(&s_next1); rt < nrt; rt = claim(&s_next1)) phase1_tile(rt);
+        }
         __syncthreads();
+        if (tid == 0) s_next1 = 1;            // phase-1 counter (tile 0 is reserved for warp 0)
         // ---- phase 3: rows below the diagonal block: X = S W^H, i.e. X[r][c] = sum_q S[r][q] conj(W[c][q])
         // local row tiles start at local row nb (nb < 16 only in the last panel, where the tile grid shifts)
         {
             const int rows3 = rows - nb;
             const int nrt3 = (rows3 + 15) >> 4;
-            for (int rt = warp; rt < nrt3; rt += CH_WARPS) {
+            for (int rt = claim(&s_next3); rt < nrt3; rt = claim(&s_next3)) {
                 const int r0 = nb + (rt << 4);
                 const int ra = min(r0 + g, rows - 1), rb8 = min(r0 + g + 8, rows - 1);
                 const cplx* pa0 = A + (size_t)(k0 + ra) * ld + k0 + tig;
