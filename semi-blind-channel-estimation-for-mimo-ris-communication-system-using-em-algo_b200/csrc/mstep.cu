@@ -504,6 +504,13 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol(Dims d, cplx* __re
                 const cplx* pa1 = A + (size_t)(k0 + rb8) * ld + tig;
                 const cplx* pb0 = A + (size_t)min(k0 + g, Ltot - 1) * ld + tig;
                 const cplx* pb1 = A + (size_t)min(k0 + 8 + g, Ltot - 1) * ld + tig;
+                // the panel block itself is only needed at the very end (S = A - acc): start fetching it now
+                if (tig == 0) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)(k0 + ra) * ld + k0));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)(k0 + ra) * ld + k0 + 8));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)(k0 + rb8) * ld + k0));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)(k0 + rb8) * ld + k0 + 8));
+                }
 #pragma unroll 2
                 for (int q0 = 0; q0 < k0; q0 += 8) {
                     const cplx a0 = pa0[q0], a1 = pa1[q0], a2 = pa0[q0 + 4], a3 = pa1[q0 + 4];
