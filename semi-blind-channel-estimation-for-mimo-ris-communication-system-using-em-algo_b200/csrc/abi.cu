@@ -39,15 +39,23 @@ struct PhaseScope {
     }
 };
 
-static int make_dims(const sbce_cfg* c, Dims* d) {
+static int make_dims(const sbce_cfg* c, Dims* d, bool with_estep = true) {
     if (!c) return SBCE_E_NULL;
     if (c->N < 1 || c->n_tx < 1 || c->n_rx < 1 || c->T_p < 0 || c->T_d < 1 || c->itera < 0 || c->batch < 0)
         return SBCE_E_SHAPE;
     int sq = 0;
     if (c->M == 4) sq = 2; else if (c->M == 16) sq = 4; else if (c->M == 64) sq = 8; else return SBCE_E_UNSUPPORTED;
-    if (c->n_tx > 4) return SBCE_E_UNSUPPORTED;
-    if (!(c->n_rx <= 4 || c->n_rx == 6 || c->n_rx == 8)) return SBCE_E_UNSUPPORTED;
+    if (c->n_tx > 8 || c->n_rx > 8) return SBCE_E_UNSUPPORTED;
+    if (c->n_tx <= 4 && !(c->n_rx <= 4 || c->n_rx == 6 || c->n_rx == 8)) return SBCE_E_UNSUPPORTED;
     if (c->mode < SBCE_MODE_SOFT || c->mode > SBCE_MODE_MMSE) return SBCE_E_UNSUPPORTED;
+    if (with_estep) {
+        // joint hypothesis indices are int32 (kstar); the exhaustive tree is instantiated up to 2^24 leaves
+        // for the wide arrays (8 streams of QPSK, 6 of 16-QAM) -- beyond that use the partitioned modes
+        const int bits = c->n_tx * (sq == 2 ? 2 : (sq == 4 ? 4 : 6));
+        const bool tree = c->mode == SBCE_MODE_SOFT || c->mode == SBCE_MODE_HARD;
+        if (tree && c->n_tx > 4 && bits > 24) return SBCE_E_UNSUPPORTED;
+        if ((c->mode == SBCE_MODE_ZF || c->mode == SBCE_MODE_MMSE) && bits > 30) return SBCE_E_UNSUPPORTED;
+    }
     d->N = c->N; d->N1 = c->N + 1; d->n_tx = c->n_tx; d->n_rx = c->n_rx; d->M = c->M; d->sqM = sq;
     d->bitsM = (sq == 2 ? 2 : (sq == 4 ? 4 : 6));
     d->T_p = c->T_p; d->T_d = c->T_d; d->itera = c->itera;
@@ -83,6 +91,7 @@ size_t carve_workspace(const Dims& d, int nb, void* base, Workspace* ws) {
     ws->active = (int32_t*)take(B * 4);
     ws->stat = (int32_t*)take(B * 4);
     ws->kscratch = (int32_t*)take(B * d.T_d * 4);
+    ws->thbuf = (double*)take(B * d.Lp * d.n_rx * 16);
     ws->bytes = off;
     return off;
 }
@@ -137,7 +146,7 @@ static int em_chunk(const Dims& d, int nb, const sbce_io& io, Workspace& ws, cud
         }
         {
             PhaseScope ps(SBCE_PHASE_CHOL, s);
-            CK(launch_chol_solve(d, nb, ws.G, io.theta, ws.active, ws.stat, s));
+            CK(launch_chol_solve(d, nb, ws.G, io.theta, ws.active, ws.stat, ws.thbuf, s));
         }
         {
             PhaseScope ps(SBCE_PHASE_METRICS, s);
@@ -200,7 +209,7 @@ const char* sbce_error_string(int code) {
         case 0: return "ok";
         case SBCE_E_NULL: return "required pointer is null";
         case SBCE_E_SHAPE: return "invalid shape parameter";
-        case SBCE_E_UNSUPPORTED: return "unsupported configuration (n_tx<=4, n_rx in {1,2,3,4,6,8}, M in {4,16,64})";
+        case SBCE_E_UNSUPPORTED: return "unsupported configuration (n_tx,n_rx<=8; n_tx<=4: n_rx in {1,2,3,4,6,8}; M in {4,16,64}; exhaustive modes with n_tx>4 need n_tx*log2(M)<=24)";
         case SBCE_E_WORKSPACE: return "workspace too small for one trial";
         case SBCE_E_NODEVICE: return "no CUDA device";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
@@ -284,7 +293,7 @@ int sbce_estep(const sbce_cfg* cfg, const sbce_io* io, const double* theta, doub
 int sbce_mstep(const sbce_cfg* cfg, const sbce_io* io, const double* stat_m, const double* stat_R, double* theta_out,
                int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
     Dims d;
-    int rc = make_dims(cfg, &d);
+    int rc = make_dims(cfg, &d, false);   // no E-step here: the hypothesis-count limits do not apply
     if (rc) return rc;
     if (!io || !io->Yd || !io->PsiD || !stat_m || !stat_R || !theta_out || !workspace) return SBCE_E_NULL;
     if (d.T_p > 0 && (!io->Yp || !io->PsiP || !io->Xp)) return SBCE_E_NULL;
@@ -303,7 +312,7 @@ int sbce_mstep(const sbce_cfg* cfg, const sbce_io* io, const double* stat_m, con
         CK(launch_normal_equations(d, nb, o.PsiP, d.T_p, o.Yp, ws.pil_m, ws.pil_R, nullptr, ws.Gp, nullptr, s));
         CK(launch_normal_equations(d, nb, o.PsiD, d.T_d, o.Yd, stat_m + sb * d.n_tx * 2,
                                    stat_R + sb * d.n_tx * d.n_tx * 2, ws.Gp, ws.G, nullptr, s));
-        CK(launch_chol_solve(d, nb, ws.G, theta_out + (size_t)b0 * d.L * d.n_rx * 2, nullptr, ws.stat, s));
+        CK(launch_chol_solve(d, nb, ws.G, theta_out + (size_t)b0 * d.L * d.n_rx * 2, nullptr, ws.stat, ws.thbuf, s));
         if (status) CK(cudaMemcpyAsync(status + b0, ws.stat, (size_t)nb * 4, cudaMemcpyDeviceToDevice, s));
     }
     return 0;

@@ -86,6 +86,7 @@ struct Workspace {
     int32_t* active;  // [nb]
     int32_t* stat;    // [nb]
     int32_t* kscratch;// [nb][T_d]
+    double* thbuf;    // [nb][Lp][n_rx] cplx  back-substitution vector when it does not fit in shared memory
     size_t bytes;
 };
 
@@ -103,7 +104,7 @@ cudaError_t launch_normal_equations(const Dims& d, int nb, const double* Psi, in
                                     const double* sm, const double* sR, const double* Ginit, double* Gout,
                                     const int32_t* active, cudaStream_t s);
 cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
-                              cudaStream_t s);
+                              double* th_scratch, cudaStream_t s);
 // metrics (metrics.cu)
 cudaError_t launch_init_state(const Dims& d, int nb, const double* theta0, double* theta, int32_t* active,
                               int32_t* stat, int32_t* iters, double* llf, double* lse, cudaStream_t s);

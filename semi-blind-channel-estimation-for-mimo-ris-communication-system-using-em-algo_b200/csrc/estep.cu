@@ -166,6 +166,100 @@ __global__ void __launch_bounds__(128) k_heff_qr(Dims d, const cplx* __restrict_
 }
 
 // ---------------------------------------------------------------------------
+// 1b. wide arrays (n_tx = 5..8): the (8 x (n_tx+1)) work matrix [Heff_t | y_t] no longer fits the
+// registers of one lane, so EIGHT lanes share a symbol, lane r owning receive row r.  The theta reads of
+// the RIS contraction are then 8 consecutive complex values per (n', j) -- one 128-byte line per symbol
+// group; the Householder inner products become 3-step xor-shuffle sums inside the aligned 8-lane group.
+// All lanes execute every shuffle (no group-divergent branches); same record layout as k_heff_qr.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double group8_sum(double v) {
+    v += shfl_xor_d(v, 4);
+    v += shfl_xor_d(v, 2);
+    v += shfl_xor_d(v, 1);
+    return v;
+}
+
+template <int NTX>
+__global__ void __launch_bounds__(128) k_heff_qr_rows(Dims d, const cplx* __restrict__ Yd,
+                                                      const cplx* __restrict__ PsiD, const cplx* __restrict__ theta,
+                                                      const int32_t* __restrict__ active, double* __restrict__ qr) {
+    const int b = blockIdx.y;
+    if (active != nullptr && active[b] == 0) return;
+    const int r = threadIdx.x & 7;
+    const int tq = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+    const bool tv = tq < d.T_d;
+    const int t = tv ? tq : d.T_d - 1;   // surplus groups redo the last symbol (they must stay in the shuffles)
+    const int nrx = d.n_rx;
+    const bool rv = r < nrx;
+    const int rr = rv ? r : 0;
+
+    const cplx* psi = PsiD + ((size_t)(d.psi_shared ? 0 : b) * d.T_d + t) * d.N1;
+    const cplx* th = theta + (size_t)b * d.L * nrx;
+
+    cplx A[NTX + 1];   // row r of [Heff | y]
+#pragma unroll
+    for (int j = 0; j <= NTX; ++j) A[j] = mk(0.0, 0.0);
+#pragma unroll 2
+    for (int n = 0; n < d.N1; ++n) {
+        const cplx p = psi[n];
+        const cplx* row = th + (size_t)n * NTX * nrx + rr;
+#pragma unroll
+        for (int j = 0; j < NTX; ++j) cfma(A[j], p, __ldg(&row[j * nrx]));
+    }
+    A[NTX] = Yd[((size_t)b * d.T_d + t) * nrx + rr];
+    if (!rv) {
+#pragma unroll
+        for (int j = 0; j <= NTX; ++j) A[j] = mk(0.0, 0.0);
+    }
+
+#pragma unroll
+    for (int k = 0; k < NTX; ++k) {
+        const double nrm2 = group8_sum(r >= k ? cnorm2(A[k]) : 0.0);
+        const bool ok = nrm2 > 0.0;
+        const double nrm = sqrt(nrm2);
+        const int src = (threadIdx.x & 24) + k;   // lane that owns row k of this group
+        const cplx a0 = mk(shfl_d(A[k].x, src), shfl_d(A[k].y, src));
+        const double abs0 = sqrt(cnorm2(a0));
+        const cplx phase = abs0 > 0.0 ? mk(a0.x / abs0, a0.y / abs0) : mk(1.0, 0.0);
+        const cplx vk = cscale(phase, abs0 + nrm);                      // v_k = phase (|a0| + ||x||)
+        const double beta = ok ? 1.0 / (nrm * (nrm + abs0)) : 0.0;      // 2 / (v^H v)
+        const cplx vr = (r == k) ? vk : (r > k ? A[k] : mk(0.0, 0.0));  // this lane's entry of v
+#pragma unroll
+        for (int c = k + 1; c <= NTX; ++c) {
+            cplx w = mk(0.0, 0.0);
+            cfmac(w, A[c], vr);   // conj(v_r) a_rc
+            w = mk(group8_sum(w.x) * beta, group8_sum(w.y) * beta);
+            const cplx nw = mk(-w.x, -w.y);
+            cfma(A[c], nw, vr);
+        }
+        if (r == k) {   // rotate row k so that its diagonal entry is +||x||
+            const cplx rot = mk(-phase.x, phase.y);
+#pragma unroll
+            for (int c = k + 1; c <= NTX; ++c) A[c] = cmul(A[c], rot);
+            A[k] = mk(ok ? nrm : 0.0, 0.0);
+        }
+    }
+    const double c0 = group8_sum(r >= NTX ? cnorm2(A[NTX]) : 0.0);
+    if (!tv) return;
+    double* rec = qr + ((size_t)b * d.T_d + t) * d.rec;
+    if (r < NTX) {
+        double* o = rec + 2 * (r * NTX - (r * (r - 1)) / 2);
+#pragma unroll
+        for (int j = 0; j < NTX; ++j)
+            if (j >= r) {
+                o[2 * (j - r)] = A[j].x;
+                o[2 * (j - r) + 1] = (j == r) ? 0.0 : A[j].y;
+            }
+        rec[NTX * (NTX + 1) + 2 * r] = A[NTX].x;
+        rec[NTX * (NTX + 1) + 2 * r + 1] = A[NTX].y;
+    }
+    if (r == 0) {
+        rec[NTX * (NTX + 1) + 2 * NTX] = c0;
+        rec[NTX * (NTX + 1) + 2 * NTX + 1] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // 2. hypothesis-tree enumeration, one warp per symbol
 // ---------------------------------------------------------------------------
 constexpr double SBCE_THR = 64.0;  // nodes whose best leaf is > THR*varn^2 above the incumbent weigh < e^-64
@@ -321,10 +415,10 @@ __device__ __noinline__ void enum_flush(double* ws, double warp_best) {
                 }
         }
         __syncwarp();
-        if (lane < E::NACC) {
+        for (int i = lane; i < E::NACC; i += 32) {
             double acc = 0.0;
-            for (int e2 = 0; e2 < nround; ++e2) acc += scr[lane * 32 + e2];
-            A[lane] += acc;
+            for (int e2 = 0; e2 < nround; ++e2) acc += scr[i * 32 + e2];
+            A[i] += acc;
         }
         __syncwarp();
     }
@@ -464,7 +558,7 @@ struct Scan {
 };
 
 template <int NTX, int SQM, bool HARD, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 4) k_enum(Dims d, const double* __restrict__ qr,
+__global__ void __launch_bounds__(WARPS * 32, (NTX > 4 ? 2 : 4)) k_enum(Dims d, const double* __restrict__ qr,
                                                      const double* __restrict__ varn,
                                                      const int32_t* __restrict__ active, cplx* __restrict__ stat_m,
                                                      cplx* __restrict__ stat_R, int32_t* __restrict__ kstar,
@@ -531,7 +625,7 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_enum(Dims d, const double* __
         ws[E::O_S2] = inv_s2;
         *(int*)(ws + E::O_CNT) = 0;
     }
-    if (lane < E::NACC) ws[E::O_ACC + lane] = 0.0;
+    for (int i = lane; i < E::NACC; i += 32) ws[E::O_ACC + i] = 0.0;
     __syncwarp();
 
     Scan<NTX, SQM, HARD> sc;
@@ -681,6 +775,27 @@ static cudaError_t run_enum(const Dims& d, int nb, const double* qr, const doubl
 }
 
 template <int NTX>
+static cudaError_t run_heff_rows(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
+                                 const int32_t* active, double* qr, cudaStream_t s) {
+    dim3 grid((d.T_d + 15) / 16, nb);   // 8 lanes per symbol, 16 symbols per CTA
+    k_heff_qr_rows<NTX><<<grid, 128, 0, s>>>(d, (const cplx*)Yd, (const cplx*)PsiD, (const cplx*)theta, active, qr);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// wide trees: only constellations whose joint hypothesis index fits comfortably in 32 bits are instantiated
+// (n_tx log2 M <= 24); abi.cu::make_dims rejects the rest before any launch
+template <int NTX>
+static cudaError_t run_enum_wide(const Dims& d, int nb, const double* qr, const double* varn, const int32_t* active,
+                                 double* stat_m, double* stat_R, int32_t* kstar, double* lse_sym, cudaStream_t s) {
+    if (d.sqM == 2) return run_enum<NTX, 2>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
+    if constexpr (NTX <= 6) {
+        if (d.sqM == 4) return run_enum<NTX, 4>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int NTX>
 static cudaError_t run_enum_ntx(const Dims& d, int nb, const double* qr, const double* varn, const int32_t* active,
                                 double* stat_m, double* stat_R, int32_t* kstar, double* lse_sym, cudaStream_t s) {
     switch (d.sqM) {
@@ -698,6 +813,10 @@ cudaError_t launch_heff_qr(const Dims& d, int nb, const double* Yd, const double
         case 2: return run_heff_ntx<2>(d, nb, Yd, PsiD, theta, active, qr, s);
         case 3: return run_heff_ntx<3>(d, nb, Yd, PsiD, theta, active, qr, s);
         case 4: return run_heff_ntx<4>(d, nb, Yd, PsiD, theta, active, qr, s);
+        case 5: return run_heff_rows<5>(d, nb, Yd, PsiD, theta, active, qr, s);
+        case 6: return run_heff_rows<6>(d, nb, Yd, PsiD, theta, active, qr, s);
+        case 7: return run_heff_rows<7>(d, nb, Yd, PsiD, theta, active, qr, s);
+        case 8: return run_heff_rows<8>(d, nb, Yd, PsiD, theta, active, qr, s);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -709,6 +828,10 @@ cudaError_t launch_enum(const Dims& d, int nb, const double* qr, const double* v
         case 2: return run_enum_ntx<2>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
         case 3: return run_enum_ntx<3>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
         case 4: return run_enum_ntx<4>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
+        case 5: return run_enum_wide<5>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
+        case 6: return run_enum_wide<6>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
+        case 7: return run_enum_wide<7>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
+        case 8: return run_enum_wide<8>(d, nb, qr, varn, active, stat_m, stat_R, kstar, lse_sym, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -10,19 +10,17 @@
 // (pilots: R = conj(x) x^T, m = conj(x)).  SURVEY.md section 8a-6.
 //
 // B200 design:
-//  * k_gram: the Kronecker / Khatri-Rao structure is applied by index
-//    arithmetic.  One thread owns one (n >= n') pair of RIS indices and
-//    accumulates the whole n_tx x n_tx block  sum_t conj(psi[t,n]) psi[t,n'] R_t
-//    in registers; psi and R_t chunks are staged in shared memory (R_t reads are
-//    warp-wide broadcasts).  Only the lower triangle is produced.  The last CTA
-//    of each trial writes B^H as RP extra rows below the matrix, and the padding.
-//  * k_chol: one CTA per trial, right-looking blocked complex Cholesky (panel
-//    width 16) on the augmented lower trapezoid [G ; B^H]: the triangular solve
-//    of the panel rows turns the B^H rows into (C^-1 B)^H for free, so only the
-//    back substitution C^H theta = z remains.  Panels live in shared memory in a
-//    micro-tile-friendly layout, the trailing update uses 4x4 complex register
-//    tiles.  A non-positive pivot flags the trial (status bit) instead of
-//    poisoning the batch.
+//  * Gram: the Kronecker / Khatri-Rao structure is applied by index arithmetic.  One (n >= n') pair of
+//    RIS indices owns the whole n_tx x n_tx block  sum_t conj(psi[t,n]) psi[t,n'] R_t ; because R_t is
+//    Hermitian its 2 n_tx^2 real accumulators are [p_r ; p_i] (2 x T) times a real (T x n_tx^2) matrix
+//    built from diag(R_t) and the upper entries, i.e. the whole Gram is ONE real GEMM that runs on the
+//    FP64 tensor path (k_gram_mma4 for n_tx = 4, k_gram_mma<NTX> for n_tx = 5..8; scalar k_gram<NTX>
+//    below 4).  Only the lower triangle is produced.  The last CTA of each trial writes B^H as extra
+//    rows below the matrix, and the padding.
+//  * k_chol: one CTA per trial, LEFT-looking blocked complex Cholesky (panel width 16) on the augmented
+//    lower trapezoid [G ; B^H], panel updates and the triangular solve as DMMA products; the B^H rows
+//    come out as (C^-1 B)^H for free, so only the back substitution C^H theta = z remains.  A
+//    non-positive pivot flags the trial (status bit) instead of poisoning the batch.
 #include <math.h>
 #include <stdlib.h>
 
@@ -393,6 +391,178 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_gram_mma4(Dims d, int T, cons
         }
 }
 
+// Generic tensor-path Gram, n_tx = 4..8.  Column layout of the real B matrix (NC columns, padded to a
+// multiple of 8): [0, NTX) the real diagonal of R_t; from the even offset PO on, (re, im) of the upper
+// entries (i<j) in row-major order.  A warp owns one 16-pair tile and all NT column tiles; the chunk
+// length TC (multiple of 8) is chosen at launch so that two cp.async stages fit in shared memory.
+template <int NTX>
+struct GramCols {
+    static constexpr int NPAIR = NTX * (NTX - 1) / 2;
+    static constexpr int PO = (NTX + 1) & ~1;
+    static constexpr int NC = PO + 2 * NPAIR;
+    static constexpr int NT = (NC + 7) / 8;
+    __device__ __forceinline__ static void pair_ij(int q, int& i, int& j) {
+        i = 0;
+        while (q >= NTX - 1 - i) { q -= NTX - 1 - i; ++i; }
+        j = i + 1 + q;
+    }
+    // column -> double offset inside the raw R_t (row-major NTX x NTX interleaved complex); -1: padding
+    __device__ __forceinline__ static int offset(int col) {
+        if (col < NTX) return 2 * (col * NTX + col);
+        if (col < PO || col >= NC) return -1;
+        int i, j;
+        pair_ij((col - PO) >> 1, i, j);
+        return 2 * (i * NTX + j) + ((col - PO) & 1);
+    }
+};
+
+constexpr int GW_PAIRS = (GR_THREADS / 32) * 16;   // pairs per CTA of the generic kernel
+
+template <int NTX>
+__global__ void __launch_bounds__(GR_THREADS, 1) k_gram_mma(Dims d, int T, int TC, const cplx* __restrict__ Psi,
+                                                          const cplx* __restrict__ sR, const cplx* __restrict__ Y,
+                                                          const cplx* __restrict__ sm, const cplx* __restrict__ Ginit,
+                                                          cplx* __restrict__ Gout, const int32_t* __restrict__ active) {
+    typedef GramCols<NTX> GC;
+    constexpr int NT = GC::NT;
+    constexpr int RS = 2 * NTX * NTX;   // doubles per staged R_t
+    extern __shared__ double2 gsm[];
+    const int b = blockIdx.y;
+    if (active != nullptr && active[b] == 0) return;
+    const int N1 = d.N1;
+    const int P = N1 * (N1 + 1) / 2;
+    const cplx* psi_b = Psi + (size_t)(d.psi_shared ? 0 : b) * T * N1;
+    const size_t gstride = (size_t)d.Ltot * d.Lp;
+    cplx* Gb = Gout + (size_t)b * gstride;
+    const cplx* Gi = Ginit ? Ginit + (size_t)b * gstride : nullptr;
+    if (blockIdx.x == gridDim.x - 1) {
+        gram_rhs_cta<NTX>(d, T, b, gsm, gsm + GR_TC * N1, psi_b, Y, sm, Gi, Gb);
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    int pn[2], pnp[2];
+    bool pv[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int item = blockIdx.x * GW_PAIRS + warp * 16 + g + 8 * h;
+        pv[h] = item < P;
+        item = min(item, P - 1);
+        int n = (int)((sqrt(8.0 * item + 1.0) - 1.0) * 0.5);
+        while ((n + 1) * (n + 2) / 2 <= item) ++n;
+        while (n * (n + 1) / 2 > item) --n;
+        pn[h] = n;
+        pnp[h] = item - n * (n + 1) / 2;
+    }
+    int boff[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) boff[nt] = GC::offset(8 * nt + g);
+    double accr[NT][4], acci[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { accr[nt][e] = 0.0; acci[nt][e] = 0.0; }
+
+    const cplx* R_b = sR + (size_t)b * T * NTX * NTX;
+    const int stage_elems = TC * (N1 + NTX * NTX);
+    auto issue = [&](int chunk, int buf) {
+        const int t0 = chunk * TC;
+        const int tc = min(TC, T - t0);
+        cplx* dpsi = gsm + buf * stage_elems;
+        cplx* dR = dpsi + TC * N1;
+        const cplx* spsi = psi_b + (size_t)t0 * N1;
+        const cplx* sRg = R_b + (size_t)t0 * NTX * NTX;
+        for (int e = threadIdx.x; e < tc * N1; e += GR_THREADS) cp_async16(dpsi + e, spsi + e);
+        for (int e = threadIdx.x; e < tc * NTX * NTX; e += GR_THREADS) cp_async16(dR + e, sRg + e);
+        if (tc < TC) {  // ragged last chunk: symbols beyond T contribute zero
+            for (int e = tc * N1 + threadIdx.x; e < TC * N1; e += GR_THREADS) dpsi[e] = mk(0.0, 0.0);
+            for (int e = tc * NTX * NTX + threadIdx.x; e < TC * NTX * NTX; e += GR_THREADS) dR[e] = mk(0.0, 0.0);
+        }
+        cp_async_commit();
+    };
+    const int nchunk = (T + TC - 1) / TC;
+    if (nchunk > 0) issue(0, 0);
+    for (int ck = 0; ck < nchunk; ++ck) {
+        const int buf = ck & 1;
+        if (ck + 1 < nchunk) { issue(ck + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        const cplx* cPsi = gsm + buf * stage_elems;
+        const double* cR = (const double*)(cPsi + TC * N1);
+        for (int ks = 0; ks < TC / 8; ++ks) {
+            const int tlo = ks * 8 + tig, thi = tlo + 4;
+            // A fragment order: (row g, t lo), (row g+8, t lo), (row g, t hi), (row g+8, t hi)
+            const cplx p0 = cmulc(cPsi[tlo * N1 + pnp[0]], cPsi[tlo * N1 + pn[0]]);
+            const cplx p1 = cmulc(cPsi[tlo * N1 + pnp[1]], cPsi[tlo * N1 + pn[1]]);
+            const cplx p2 = cmulc(cPsi[thi * N1 + pnp[0]], cPsi[thi * N1 + pn[0]]);
+            const cplx p3 = cmulc(cPsi[thi * N1 + pnp[1]], cPsi[thi * N1 + pn[1]]);
+            const double pr[4] = {p0.x, p1.x, p2.x, p3.x};
+            const double pi[4] = {p0.y, p1.y, p2.y, p3.y};
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double b0 = boff[nt] >= 0 ? cR[tlo * RS + boff[nt]] : 0.0;
+                const double b1 = boff[nt] >= 0 ? cR[thi * RS + boff[nt]] : 0.0;
+                dmma16x8x8(accr[nt], pr, b0, b1);
+                dmma16x8x8(acci[nt], pi, b0, b1);
+            }
+        }
+        __syncthreads();
+    }
+    // epilogue: accumulator (row g + 8h, cols 8 nt + 2 tig, + 1)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (!pv[h]) continue;
+        const int n = pn[h], np = pnp[h];
+        auto put = [&](int i, int j, cplx v) {
+            const size_t o = (size_t)(n * NTX + i) * d.Lp + (np * NTX + j);
+            if (Gi) v = cadd(v, Gi[o]);
+            Gb[o] = v;
+        };
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const double r0 = accr[nt][2 * h], r1 = accr[nt][2 * h + 1];
+            const double i0 = acci[nt][2 * h], i1 = acci[nt][2 * h + 1];
+            const int col = 8 * nt + 2 * tig;
+            if (col < NTX) {  // diagonal entries: (pr Rd, pi Rd)
+                put(col, col, mk(r0, i0));
+                if (col + 1 < NTX) put(col + 1, col + 1, mk(r1, i1));
+            } else if (col >= GC::PO && col < GC::NC) {  // upper pair: U = pr Rr, W = pr Ri, Z = pi Rr, V = pi Ri
+                int qi, qj;
+                GC::pair_ij((col - GC::PO) >> 1, qi, qj);
+                put(qi, qj, mk(r0 - i1, r1 + i0));
+                put(qj, qi, mk(r0 + i1, i0 - r1));
+            }
+        }
+    }
+}
+
+// largest chunk length (multiple of 8, at most 32) whose two stages fit in `budget` bytes
+static int gram_chunk(int N1, int ntx, size_t budget) {
+    int tc = 32;
+    while (tc > 8 && sizeof(cplx) * (size_t)(2 * tc * (N1 + ntx * ntx)) > budget) tc >>= 1;
+    return tc;
+}
+
+template <int NTX>
+static cudaError_t run_gram_wide(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Y,
+                                 const double* sm, const double* Ginit, double* Gout, const int32_t* active,
+                                 cudaStream_t s) {
+    const int P = d.N1 * (d.N1 + 1) / 2;
+    dim3 grid((P + GW_PAIRS - 1) / GW_PAIRS + 1, nb);   // + 1: the right-hand-side / padding CTA
+    const int tc = gram_chunk(d.N1, NTX, 100 * 1024);
+    const int zsz = NTX * (d.n_rx > NTX ? d.n_rx : NTX);
+    size_t smem = sizeof(cplx) * (size_t)(2 * tc * (d.N1 + NTX * NTX));
+    const size_t smem_rhs = sizeof(cplx) * (size_t)(GR_TC * d.N1 + GR_TC * zsz);
+    if (smem_rhs > smem) smem = smem_rhs;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_gram_mma<NTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_gram_mma<NTX><<<grid, GR_THREADS, smem, s>>>(d, T, tc, (const cplx*)Psi, (const cplx*)sR, (const cplx*)Y,
+                                                   (const cplx*)sm, (const cplx*)Ginit, (cplx*)Gout, active);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int NTX>
 static cudaError_t run_gram(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Y,
                             const double* sm, const double* Ginit, double* Gout, const int32_t* active,
@@ -403,6 +573,7 @@ static cudaError_t run_gram(const Dims& d, int nb, const double* Psi, int T, con
     size_t smem = sizeof(cplx) * (size_t)(2 * GR_TC * (d.N1 + NTX * NTX));          // two cp.async stages (pair CTAs)
     const size_t smem_rhs = sizeof(cplx) * (size_t)(GR_TC * d.N1 + GR_TC * zsz);     // rhs CTA, single stage
     if (smem_rhs > smem) smem = smem_rhs;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_gram<NTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -412,6 +583,8 @@ static cudaError_t run_gram(const Dims& d, int nb, const double* Psi, int T, con
         const char* v = getenv("SBCE_GRAM_SCALAR");
         use_mma = (v && atoi(v)) ? 0 : 1;
     }
+    if (NTX == 4 && use_mma && sizeof(cplx) * (size_t)(2 * GM_TC * (d.N1 + NTX * NTX)) > 160 * 1024)
+        return run_gram_wide<4>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
     if (NTX == 4 && use_mma) {
         const size_t smem_mma = sizeof(cplx) * (size_t)(2 * GM_TC * (d.N1 + NTX * NTX));
         if (smem_mma > smem) smem = smem_mma;
@@ -439,6 +612,10 @@ cudaError_t launch_normal_equations(const Dims& d, int nb, const double* Psi, in
         case 2: return run_gram<2>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
         case 3: return run_gram<3>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
         case 4: return run_gram<4>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
+        case 5: return run_gram_wide<5>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
+        case 6: return run_gram_wide<6>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
+        case 7: return run_gram_wide<7>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
+        case 8: return run_gram_wide<8>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -466,7 +643,7 @@ template <int CH_THREADS, int CH_MINB>
 __global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol(Dims d, cplx* __restrict__ Gall,
                                                               cplx* __restrict__ theta,
                                                               const int32_t* __restrict__ active,
-                                                              int32_t* __restrict__ stat) {
+                                                              int32_t* __restrict__ stat, cplx* th_global) {
     constexpr int CH_WARPS = CH_THREADS / 32;
     extern __shared__ double2 csm[];
     const int b = blockIdx.x;
@@ -478,7 +655,9 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol(Dims d, cplx* __re
 
     cplx* sD = csm;                   // [16][17] diagonal block factor (later: reduction scratch)
     cplx* sW = sD + CH_NB * CH_DS;    // [16][17] its inverse
-    cplx* th = sW + CH_NB * CH_DS;    // [Lp][n_rx] solution during the back substitution
+    // [Lp][n_rx] solution during the back substitution: shared memory, or (very long channels) a
+    // per-trial global scratch -- CTA barriers order its accesses just the same
+    cplx* th = th_global ? th_global + (size_t)b * d.Lp * d.n_rx : sW + CH_NB * CH_DS;
     __shared__ int s_bad, s_next1, s_next3;
     if (tid == 0) { s_bad = 0; s_next1 = 1; s_next3 = 0; }
 
@@ -722,7 +901,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol(Dims d, cplx* __re
 
 template <int T, int MB>
 static cudaError_t run_chol(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
-                            size_t smem, cudaStream_t s) {
+                            size_t smem, double* thg, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(k_chol<T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     static int wave = -1;
@@ -734,17 +913,23 @@ static cudaError_t run_chol(const Dims& d, int nb, double* G, double* theta, con
     for (int b0 = 0; b0 < nb; b0 += step) {
         const int n = (nb - b0 < step) ? nb - b0 : step;
         k_chol<T, MB><<<n, T, smem, s>>>(d, (cplx*)G + (size_t)b0 * d.Ltot * d.Lp, (cplx*)theta + (size_t)b0 * d.L * d.n_rx,
-                                         active ? active + b0 : nullptr, stat ? stat + b0 : nullptr);
+                                         active ? active + b0 : nullptr, stat ? stat + b0 : nullptr,
+                                         thg ? (cplx*)thg + (size_t)b0 * d.Lp * d.n_rx : nullptr);
         count_launch();
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
-                              cudaStream_t s) {
+                              double* th_scratch, cudaStream_t s) {
     size_t thsz = (size_t)d.Lp * d.n_rx;
     size_t smem = sizeof(cplx) * (2 * CH_NB * CH_DS + thsz);
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    double* thg = nullptr;
+    if (smem > 48 * 1024) {   // keep four trials resident per SM: the solution vector moves to global scratch
+        if (!th_scratch) return cudaErrorInvalidValue;
+        thg = th_scratch;
+        smem = sizeof(cplx) * (2 * CH_NB * CH_DS);
+    }
     // CTA shape (SBCE_CHOL_VARIANT selects alternatives for experiments)
     static int variant = -1;
     if (variant < 0) {
@@ -754,11 +939,11 @@ cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, c
     // measured on B200 (N=64, 4x4: L=260, 592 trials): 128x4 1.40 ms, 256x2 2.0 ms, 288x1 2.9 ms -- the kernel
     // is latency bound, more resident trials per SM win even though their factors no longer all fit in L2
     switch (variant) {
-        case 2: return run_chol<256, 2>(d, nb, G, theta, active, stat, smem, s);
-        case 3: return run_chol<288, 1>(d, nb, G, theta, active, stat, smem, s);
-        case 4: return run_chol<64, 8>(d, nb, G, theta, active, stat, smem, s);
-        case 5: return run_chol<96, 5>(d, nb, G, theta, active, stat, smem, s);
-        default: return run_chol<128, 4>(d, nb, G, theta, active, stat, smem, s);
+        case 2: return run_chol<256, 2>(d, nb, G, theta, active, stat, smem, thg, s);
+        case 3: return run_chol<288, 1>(d, nb, G, theta, active, stat, smem, thg, s);
+        case 4: return run_chol<64, 8>(d, nb, G, theta, active, stat, smem, thg, s);
+        case 5: return run_chol<96, 5>(d, nb, G, theta, active, stat, smem, thg, s);
+        default: return run_chol<128, 4>(d, nb, G, theta, active, stat, smem, thg, s);
     }
 }
 

@@ -22,10 +22,12 @@
 
 namespace sbce {
 
-constexpr int PM_MAXT = 4;
-constexpr int PM_MAXR = 8;
+constexpr int PM_MAXR = 8;   // receive antennas
+// PM_MAXT (template parameter of everything below): 4 for n_tx <= 4, 8 for the wide arrays, so that the
+// per-lane scratch of the common small configurations stays small
 
 // Cholesky of the k x k Hermitian matrix A (row-major, stride PM_MAXT) in place (lower); returns false if not PD
+template <int PM_MAXT>
 __device__ bool small_chol(cplx (*A)[PM_MAXT], int k) {
     bool ok = true;
     for (int c = 0; c < k; ++c) {
@@ -44,6 +46,7 @@ __device__ bool small_chol(cplx (*A)[PM_MAXT], int k) {
 }
 
 // diag of inv(A) given its Cholesky factor Lc (lower): W = Lc^-1, diag_i = sum_{q>=i} |W[q][i]|^2
+template <int PM_MAXT>
 __device__ void inv_diag_from_chol(cplx (*Lc)[PM_MAXT], int k, double* dg) {
     cplx W[PM_MAXT][PM_MAXT];
     for (int c = 0; c < k; ++c) {
@@ -81,6 +84,7 @@ __device__ int slice_qam(cplx z, int sqM, int hb) {
     return (bq << hb) | bi;
 }
 
+template <int PM_MAXT>
 __global__ void __launch_bounds__(128) k_pm_stats(Dims d, const cplx* __restrict__ Yd, const cplx* __restrict__ PsiD,
                                                   const cplx* __restrict__ theta, const double* __restrict__ varn,
                                                   const int32_t* __restrict__ active, cplx* __restrict__ stat_m,
@@ -326,10 +330,14 @@ __global__ void __launch_bounds__(128) k_pm_stats(Dims d, const cplx* __restrict
 cudaError_t launch_pm_stats(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
                             const double* varn, const int32_t* active, double* stat_m, double* stat_R,
                             int32_t* kstar, cudaStream_t s) {
-    if (d.n_tx > PM_MAXT || d.n_rx > PM_MAXR) return cudaErrorInvalidValue;
+    if (d.n_tx > 8 || d.n_rx > PM_MAXR) return cudaErrorInvalidValue;
     dim3 grid((d.T_d + 3) / 4, nb);
-    k_pm_stats<<<grid, 128, 0, s>>>(d, (const cplx*)Yd, (const cplx*)PsiD, (const cplx*)theta, varn, active,
-                                    (cplx*)stat_m, (cplx*)stat_R, kstar);
+    if (d.n_tx <= 4)
+        k_pm_stats<4><<<grid, 128, 0, s>>>(d, (const cplx*)Yd, (const cplx*)PsiD, (const cplx*)theta, varn, active,
+                                           (cplx*)stat_m, (cplx*)stat_R, kstar);
+    else
+        k_pm_stats<8><<<grid, 128, 0, s>>>(d, (const cplx*)Yd, (const cplx*)PsiD, (const cplx*)theta, varn, active,
+                                           (cplx*)stat_m, (cplx*)stat_R, kstar);
     count_launch();
     return cudaGetLastError();
 }

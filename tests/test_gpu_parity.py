@@ -37,6 +37,9 @@ ESTEP_CASES = [
     (8, 2, 2, 4, 33, 0.1), (8, 2, 2, 4, 33, 3.0), (8, 2, 4, 16, 17, 0.3), (6, 2, 3, 64, 9, 0.5),
     (7, 3, 3, 4, 21, 0.2), (5, 3, 4, 16, 10, 1.5), (5, 3, 2, 4, 10, 0.7),
     (9, 4, 4, 4, 19, 0.1), (6, 4, 4, 16, 6, 0.5), (6, 4, 4, 16, 6, 30.0), (4, 4, 6, 4, 7, 0.4), (4, 2, 8, 4, 7, 0.4),
+    # wide arrays (BASELINE.json configs 4/5: 8x8): row-per-lane QR + deep hypothesis trees
+    (6, 5, 5, 4, 9, 0.3), (5, 6, 6, 4, 7, 0.2), (5, 7, 8, 4, 6, 0.4), (6, 8, 8, 4, 9, 0.3), (6, 8, 8, 4, 5, 20.0),
+    (4, 5, 6, 16, 3, 0.6), (4, 6, 4, 4, 5, 0.5), (5, 5, 7, 4, 18, 0.2),
 ]
 
 
@@ -125,7 +128,13 @@ def test_estep_zero_theta_is_uniform_posterior(S, orc):
 
 
 MSTEP_CASES = [(8, 2, 2, 4, 12, 30), (32, 2, 2, 4, 40, 50), (6, 1, 4, 16, 8, 20), (5, 3, 3, 4, 14, 16),
-               (16, 4, 4, 16, 24, 80), (11, 3, 2, 4, 20, 40), (64, 4, 4, 4, 64, 256)]
+               (16, 4, 4, 16, 24, 80), (11, 3, 2, 4, 20, 40), (64, 4, 4, 4, 64, 256),
+               # wide arrays: generic tensor-path Gram (n_tx = 5..8)
+               (6, 5, 5, 4, 20, 40), (7, 6, 8, 4, 24, 50), (5, 7, 7, 4, 30, 41), (9, 8, 8, 4, 50, 77),
+               (12, 8, 8, 16, 60, 120),
+               # long channels: n_tx = 4 beyond the fixed-chunk Gram kernel (N = 256), and a solution vector
+               # that no longer fits in shared memory (L = 1288, n_rx = 8 -> global scratch)
+               (256, 4, 2, 4, 600, 800), (256, 2, 2, 4, 300, 400), (160, 8, 8, 4, 800, 900)]
 
 
 @pytest.mark.parametrize("case", MSTEP_CASES)
@@ -136,13 +145,15 @@ def test_mstep_matches_oracle(S, orc, case):
     B = 2
     tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, 0.1, B, seed=5, legacy=False)
     cons = orc.qam_constellation(M)
-    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=1)
+    # (the M-step does not depend on the mode; 8 streams of 16-QAM only exist in the partitioned modes)
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=1,
+                     mode="soft" if n_tx * np.log2(M) <= 24 else "pm_beta")
     # soft statistics from a perturbed theta so R_t is full-rank-ish; computed by the oracle
     # (for the 64x4x4 case use rank-one statistics of the true symbols to keep the CPU side fast)
     sm = np.empty((B, T_d, n_tx), np.complex128)
     sR = np.empty((B, T_d, n_tx, n_tx), np.complex128)
     for b in range(B):
-        if M ** n_tx <= 4096:
+        if M ** n_tx <= 4096 or (n_tx > 4 and N < 10 and M == 4):
             sm[b], sR[b], _, _ = orc.posterior_stats(tb.Yd[b], tb.PsiD[b], 0.7 * tb.h[b], cons, n_tx, 2.0)
         else:
             sm[b], sR[b] = orc.pilot_stats(tb.Xd[b])
@@ -251,13 +262,17 @@ BATCH_CASES = [
     (12, 4, 4, 4, 32, 64, 3, 0.2, "soft"),
     (8, 4, 4, 16, 24, 40, 2, 0.5, "soft"),
     (8, 4, 4, 16, 24, 40, 2, 0.5, "hard"),
+    (6, 8, 8, 4, 64, 80, 2, 0.3, "soft"),        # 8x8 QPSK (K = 65536), BASELINE.json config 4
+    (6, 8, 8, 4, 64, 80, 2, 0.3, "hard"),
+    (5, 6, 8, 4, 40, 50, 3, 0.5, "soft"),
+    (4, 5, 5, 16, 30, 10, 2, 0.8, "soft"),       # 5 streams of 16-QAM: K = 2^20
 ]
 
 
 @pytest.mark.parametrize("case", BATCH_CASES)
 def test_em_batch_matches_oracle(S, orc, case):
     N, n_tx, n_rx, M, T_p, T_d, itera, varn, mode = case
-    B = 4
+    B = 4 if M ** n_tx <= 4096 else 2      # the oracle enumerates all K hypotheses per symbol
     tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn, B, seed=42, legacy=False)
     prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera, mode=mode)
     res = S.run_host(prob, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, tb.varn, theta0=tb.theta0, h_true=tb.h,
@@ -340,6 +355,9 @@ PM_CASES = [
     (8, 3, 3, 4, 8, 40, 3, 0.3, "pm_beta", 2, True), (8, 3, 4, 16, 8, 40, 2, 0.5, "pm_beta", 4, False),
     (6, 4, 4, 4, 6, 48, 2, 0.3, "pm", 2, True), (6, 4, 4, 16, 6, 48, 2, 0.6, "pm_beta", 4, False),
     (6, 2, 4, 16, 6, 30, 2, 0.6, "pm_beta", 4, True),   # p+1 = n_tx: no zero-forced streams
+    # wide arrays, BASELINE.json configs 4/5: 8x8 16-QAM is only tractable with the partition (p+1 = 2 -> 256 candidates)
+    (6, 8, 8, 16, 6, 70, 2, 0.6, "pm_beta", 4, False), (6, 8, 8, 16, 6, 70, 2, 0.6, "pm_beta", 4, True),
+    (6, 6, 8, 4, 6, 60, 2, 0.4, "pm", 2, True), (5, 5, 5, 64, 5, 40, 2, 0.8, "pm_beta", 6, False),
 ]
 
 
@@ -375,7 +393,9 @@ def test_em_zf_mmse_golden(S, orc, name):
 
 @pytest.mark.parametrize("case", [(8, 2, 2, 4, 8, 30, 3, 0.3, "zf", True), (8, 2, 2, 4, 8, 30, 3, 0.3, "mmse", True),
                                   (8, 3, 3, 4, 8, 30, 3, 0.5, "zf", False), (6, 4, 4, 16, 6, 40, 2, 0.5, "mmse", False),
-                                  (6, 2, 4, 16, 6, 30, 3, 1.0, "zf", True), (6, 3, 4, 4, 6, 30, 3, 2.0, "mmse", True)])
+                                  (6, 2, 4, 16, 6, 30, 3, 1.0, "zf", True), (6, 3, 4, 4, 6, 30, 3, 2.0, "mmse", True),
+                                  (6, 8, 8, 4, 6, 70, 2, 0.5, "zf", False), (6, 6, 8, 16, 6, 60, 2, 0.5, "mmse", False),
+                                  (6, 5, 6, 4, 6, 50, 2, 0.5, "mmse", True)])
 def test_em_detector_batch_matches_oracle(S, orc, case):
     N, n_tx, n_rx, M, T_p, T_d, itera, varn, mode, quirks = case
     B = 4

@@ -40,9 +40,15 @@ def test_workspace_query_and_argument_errors_need_no_gpu():
     one = sbce.engine.workspace_bytes(prob, 1)
     many = sbce.engine.workspace_bytes(prob, 100)
     assert 2.0e6 < one < 3.5e6 and 95 * one < many < 105 * one
-    bad = sbce.Problem(N=8, n_tx=5, n_rx=2, M=4, T_p=8, T_d=8, itera=1)
-    with pytest.raises(sbce.SbceError):
-        sbce.engine.workspace_bytes(bad, 1)
+    assert sbce.engine.workspace_bytes(sbce.Problem(N=8, n_tx=8, n_rx=8, M=4, T_p=8, T_d=8, itera=1), 1) > 0
+    for bad in (sbce.Problem(N=8, n_tx=9, n_rx=2, M=4, T_p=8, T_d=8, itera=1),          # more than 8 streams
+                sbce.Problem(N=8, n_tx=8, n_rx=8, M=16, T_p=8, T_d=8, itera=1),         # 2^32 joint hypotheses
+                sbce.Problem(N=8, n_tx=3, n_rx=5, M=4, T_p=8, T_d=8, itera=1)):
+        with pytest.raises(sbce.SbceError):
+            sbce.engine.workspace_bytes(bad, 1)
+    # ... which the partitioned mode handles (BASELINE.json config 5)
+    assert sbce.engine.workspace_bytes(sbce.Problem(N=8, n_tx=8, n_rx=8, M=16, T_p=8, T_d=8, itera=1, mode="pm_beta",
+                                                    partition_r=4), 1) > 0
     bad = sbce.Problem(N=8, n_tx=2, n_rx=2, M=8, T_p=8, T_d=8, itera=1)
     with pytest.raises(sbce.SbceError):
         sbce.engine.workspace_bytes(bad, 1)
