@@ -356,7 +356,8 @@ PM_CASES = [
     (6, 4, 4, 4, 6, 48, 2, 0.3, "pm", 2, True), (6, 4, 4, 16, 6, 48, 2, 0.6, "pm_beta", 4, False),
     (6, 2, 4, 16, 6, 30, 2, 0.6, "pm_beta", 4, True),   # p+1 = n_tx: no zero-forced streams
     # wide arrays, BASELINE.json configs 4/5: 8x8 16-QAM is only tractable with the partition (p+1 = 2 -> 256 candidates)
-    (6, 8, 8, 16, 6, 70, 2, 0.6, "pm_beta", 4, False), (6, 8, 8, 16, 6, 70, 2, 0.6, "pm_beta", 4, True),
+    # (T_p >= n_tx: the min-norm LS start has rank <= T_p, below that the zero-forcing matrices are singular)
+    (6, 8, 8, 16, 16, 70, 2, 0.6, "pm_beta", 4, False), (6, 8, 8, 16, 16, 70, 2, 0.6, "pm_beta", 4, True),
     (6, 6, 8, 4, 6, 60, 2, 0.4, "pm", 2, True), (5, 5, 5, 64, 5, 40, 2, 0.8, "pm_beta", 6, False),
 ]
 
@@ -394,7 +395,7 @@ def test_em_zf_mmse_golden(S, orc, name):
 @pytest.mark.parametrize("case", [(8, 2, 2, 4, 8, 30, 3, 0.3, "zf", True), (8, 2, 2, 4, 8, 30, 3, 0.3, "mmse", True),
                                   (8, 3, 3, 4, 8, 30, 3, 0.5, "zf", False), (6, 4, 4, 16, 6, 40, 2, 0.5, "mmse", False),
                                   (6, 2, 4, 16, 6, 30, 3, 1.0, "zf", True), (6, 3, 4, 4, 6, 30, 3, 2.0, "mmse", True),
-                                  (6, 8, 8, 4, 6, 70, 2, 0.5, "zf", False), (6, 6, 8, 16, 6, 60, 2, 0.5, "mmse", False),
+                                  (6, 8, 8, 4, 16, 70, 2, 0.5, "zf", False), (6, 6, 8, 16, 6, 60, 2, 0.5, "mmse", False),
                                   (6, 5, 6, 4, 6, 50, 2, 0.5, "mmse", True)])
 def test_em_detector_batch_matches_oracle(S, orc, case):
     N, n_tx, n_rx, M, T_p, T_d, itera, varn, mode, quirks = case
