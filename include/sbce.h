@@ -152,6 +152,46 @@ int sbce_mstep(const sbce_cfg* cfg, const sbce_io* io, const double* stat_m, con
 int sbce_accumulate_nmse(const double* nmse, const int32_t* status, int32_t batch, double* acc,
                          void* stream);
 
+/* ---- on-device input generation and LS start (the step right before the hot path) ------------------
+ * Replaces, for Monte-Carlo sweeps, the reference's per-trial host generation
+ *     channelMatrix / symbols / pilotSymbols   /root/reference/Proposed method/PM.py:11-40
+ *     irsMatrix (+ inserted ones row)          /root/reference/Proposed method/PM.py:119-130,179
+ *     receivedSignals (Y = Z h + n, h_initial) /root/reference/Proposed method/PM.py:132-148
+ * Counter-based Philox4x32-10 keyed by `seed`; element e of array a of global trial (trial0 + b) is
+ * Philox(counter = (e, a, trial), key = seed), so results do not depend on batch size or sharding
+ * (oracle/philox.py restates the generator in numpy; symbol indices are bit-exact). */
+#define SBCE_PILOTS_PM 0     /* exp(-j2pi t n/N), n<N, in rows 0..N-1, row N zero (PM.py:120-124)                */
+#define SBCE_PILOTS_TOP 1    /* ones row + exp(-j2pi t n/T_p) (Proposed_method_NMSEvsTp.py:72-83,129)           */
+#define SBCE_PHASES_RANDOM 0 /* ones row + exp(j U(0,2pi)) per (trial, symbol, element) (PM.py:125-129,179)     */
+#define SBCE_PHASES_DFT 1    /* exp(-j2pi t n/T_d) over n = 0..N (Proposed_method_NMSEvsTd.py:92-94)            */
+
+typedef struct sbce_gen {
+    uint64_t seed;        /* Philox key                                                        */
+    int64_t trial0;       /* global index of the first trial of this batch (disjoint per rank) */
+    int32_t pilot_design; /* SBCE_PILOTS_*                                                     */
+    int32_t data_phases;  /* SBCE_PHASES_*                                                     */
+    double varh;          /* channel variance (reference: 1)                                   */
+    int32_t reserved[4];
+} sbce_gen;
+
+/* Fills the caller's DEVICE buffers io->h_true, Xp, Xd_true, PsiP, PsiD, Yp, Yd (declared const in
+ * sbce_io because the estimator only reads them; here they are written) for cfg->batch trials;
+ * reads io->varn [B].  With SBCE_FLAG_PSI_SHARED the phase arrays have no batch dimension. */
+int sbce_generate_batch(const sbce_cfg* cfg, const sbce_gen* gen, const sbce_io* io, void* stream);
+
+/* LS start h_initial = pinv(Z_p) y_p (PM.py:147) for every trial: min-norm solution through the
+ * T_p x T_p Gram (Psi Psi^H) o (X X^H) when T_p < L, pilot normal equations when T_p >= L.
+ * Reads io->Yp, PsiP, Xp; writes theta0 [B][L][n_rx]; status (nullable) gets SBCE_ST_NOT_PD for
+ * rank-deficient pilot blocks (where pinv would invert rounding noise).  Workspace as sbce_em_batch. */
+int sbce_ls_start(const sbce_cfg* cfg, const sbce_io* io, double* theta0, int32_t* status, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* Symbol-error accumulation for the SER drivers (SER/log_max_SER.py:162): acc[0] += per-stream symbol
+ * errors, acc[1] += symbols compared, acc[2] += sum over trials of the as-coded SER (the reference's
+ * (T,n,1)-(T,1,n) broadcast).  kstar [B][T_d] int32, Xd_true [B][T_d][n_tx] complex128, acc 3 float64. */
+int sbce_accumulate_ser(const sbce_cfg* cfg, const int32_t* kstar, const double* Xd_true, int32_t batch, double* acc,
+                        void* stream);
+
 /* Measured FP64 FMA throughput of the current device (TFLOP/s, 2 flops per
  * FMA), used as the roofline denominator for the FP64-bound kernels. */
 int sbce_measure_fp64_peak(double* tflops, double* seconds);

@@ -36,10 +36,19 @@ class Io(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _IO_FIELDS]
 
 
+class Gen(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("trial0", C.c_int64), ("pilot_design", C.c_int32), ("data_phases", C.c_int32),
+                ("varh", C.c_double), ("reserved", C.c_int32 * 4)]
+
+
+PILOTS = {"pm": 0, "top": 1, "top_tp": 1, "top_td": 1}
+PHASES_KIND = {"random": 0, "dft": 1}
+
 # every symbol include/sbce.h declares; tests assert the library exports all of them
 EXPORTS = ["sbce_version", "sbce_error_string", "sbce_device_count", "sbce_workspace_bytes", "sbce_em_batch",
            "sbce_em_batch_host", "sbce_estep", "sbce_mstep", "sbce_accumulate_nmse", "sbce_measure_fp64_peak",
-           "sbce_launch_count", "sbce_profile_begin", "sbce_profile_end"]
+           "sbce_launch_count", "sbce_profile_begin", "sbce_profile_end", "sbce_generate_batch", "sbce_ls_start",
+           "sbce_accumulate_ser"]
 
 PHASES = ["setup", "heff_qr", "enum", "gram", "rhs", "chol", "metrics"]
 
@@ -67,6 +76,10 @@ def load():
     lib.sbce_mstep.argtypes = [C.POINTER(Cfg), C.POINTER(Io), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_size_t, C.c_void_p]
     lib.sbce_accumulate_nmse.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.sbce_generate_batch.argtypes = [C.POINTER(Cfg), C.POINTER(Gen), C.POINTER(Io), C.c_void_p]
+    lib.sbce_ls_start.argtypes = [C.POINTER(Cfg), C.POINTER(Io), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                  C.c_void_p]
+    lib.sbce_accumulate_ser.argtypes = [C.POINTER(Cfg), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.sbce_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.sbce_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
     lib.sbce_launch_count.restype = C.c_int64

@@ -92,6 +92,9 @@ size_t carve_workspace(const Dims& d, int nb, void* base, Workspace* ws) {
     ws->stat = (int32_t*)take(B * 4);
     ws->kscratch = (int32_t*)take(B * d.T_d * 4);
     ws->thbuf = (double*)take(B * d.Lp * d.n_rx * 16);
+    ws->psiw = (double*)take(B * d.T_p * d.N1 * 16 + 16);
+    ws->ls_scale = (double*)take(B * d.N1 * 8);
+    ws->ls_rep = (int32_t*)take(B * d.N1 * 4);
     ws->bytes = off;
     return off;
 }
@@ -321,6 +324,53 @@ int sbce_mstep(const sbce_cfg* cfg, const sbce_io* io, const double* stat_m, con
 int sbce_accumulate_nmse(const double* nmse, const int32_t* status, int32_t batch, double* acc, void* stream) {
     if (!nmse || !acc) return SBCE_E_NULL;
     CK(launch_accumulate_nmse(nmse, status, batch, acc, (cudaStream_t)stream));
+    return 0;
+}
+
+int sbce_generate_batch(const sbce_cfg* cfg, const sbce_gen* gen, const sbce_io* io, void* stream) {
+    Dims d;
+    int rc = make_dims(cfg, &d, false);
+    if (rc) return rc;
+    if (!gen || !io) return SBCE_E_NULL;
+    if (!io->h_true || !io->Xd_true || !io->PsiD || !io->Yd || !io->varn) return SBCE_E_NULL;
+    if (d.T_p > 0 && (!io->Xp || !io->PsiP || !io->Yp)) return SBCE_E_NULL;
+    if (gen->pilot_design < SBCE_PILOTS_PM || gen->pilot_design > SBCE_PILOTS_TOP) return SBCE_E_UNSUPPORTED;
+    if (gen->data_phases < SBCE_PHASES_RANDOM || gen->data_phases > SBCE_PHASES_DFT) return SBCE_E_UNSUPPORTED;
+    if (cfg->batch == 0) return 0;
+    CK(launch_generate(d, cfg->batch, gen, *io, (double*)io->h_true, (double*)io->Xp, (double*)io->Xd_true,
+                       (double*)io->PsiP, (double*)io->PsiD, (double*)io->Yp, (double*)io->Yd, (cudaStream_t)stream));
+    return 0;
+}
+
+int sbce_ls_start(const sbce_cfg* cfg, const sbce_io* io, double* theta0, int32_t* status, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+    Dims d;
+    int rc = make_dims(cfg, &d, false);
+    if (rc) return rc;
+    if (!io || !io->Yp || !io->PsiP || !io->Xp || !theta0 || !workspace) return SBCE_E_NULL;
+    if (d.T_p < 1) return SBCE_E_SHAPE;
+    if (cfg->batch == 0) return 0;
+    const int chunk = trials_fitting(d, workspace_bytes, cfg->batch);
+    if (chunk < 1) return SBCE_E_WORKSPACE;
+    for (int b0 = 0; b0 < cfg->batch; b0 += chunk) {
+        const int nb = (cfg->batch - b0 < chunk) ? cfg->batch - b0 : chunk;
+        Workspace ws;
+        carve_workspace(d, nb, workspace, &ws);
+        sbce_io o = offset_io(d, *io, (size_t)b0);
+        CK(launch_ls_start(d, nb, o, theta0 + (size_t)b0 * d.L * d.n_rx * 2, status ? status + b0 : nullptr, ws,
+                           (cudaStream_t)stream));
+    }
+    return 0;
+}
+
+int sbce_accumulate_ser(const sbce_cfg* cfg, const int32_t* kstar, const double* Xd_true, int32_t batch, double* acc,
+                        void* stream) {
+    Dims d;
+    int rc = make_dims(cfg, &d, false);
+    if (rc) return rc;
+    if (!kstar || !Xd_true || !acc) return SBCE_E_NULL;
+    if (d.n_tx * d.bitsM > 30) return SBCE_E_UNSUPPORTED;
+    CK(launch_accumulate_ser(d, batch, kstar, Xd_true, acc, (cudaStream_t)stream));
     return 0;
 }
 

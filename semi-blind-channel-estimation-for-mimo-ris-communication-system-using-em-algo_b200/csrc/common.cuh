@@ -86,6 +86,9 @@ struct Workspace {
     int32_t* active;  // [nb]
     int32_t* stat;    // [nb]
     int32_t* kscratch;// [nb][T_d]
+    double* psiw;     // [nb][T_p][N+1] cplx  LS start: pilot phases with identical columns merged
+    double* ls_scale; // [nb][N+1]  sqrt(multiplicity) of a kept column, 0 for a removed one
+    int32_t* ls_rep;  // [nb][N+1]  representative column (-1: zero column)
     double* thbuf;    // [nb][Lp][n_rx] cplx  back-substitution vector when it does not fit in shared memory
     size_t bytes;
 };
@@ -116,6 +119,14 @@ cudaError_t launch_final_metrics(const Dims& d, int nb, const double* theta, con
                                  double* nmse, int32_t* status, cudaStream_t s);
 cudaError_t launch_accumulate_nmse(const double* nmse, const int32_t* status, int batch, double* acc, cudaStream_t s);
 cudaError_t run_fp64_peak(double* tflops, double* seconds);
+// generation + LS start (gen.cu)
+cudaError_t launch_generate(const Dims& d, int nb, const sbce_gen* g, const sbce_io& io, double* h_out, double* Xp_out,
+                            double* Xd_out, double* PsiP_out, double* PsiD_out, double* Yp_out, double* Yd_out,
+                            cudaStream_t s);
+cudaError_t launch_ls_start(const Dims& d, int nb, const sbce_io& io, double* theta0, int32_t* status, Workspace& ws,
+                            cudaStream_t s);
+cudaError_t launch_accumulate_ser(const Dims& d, int nb, const int32_t* kstar, const double* Xd, double* acc,
+                                  cudaStream_t s);
 
 void count_launch(int n = 1);
 

@@ -661,6 +661,7 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol(Dims d, cplx* __re
     __shared__ int s_bad, s_next1, s_next3;
     if (tid == 0) { s_bad = 0; s_next1 = 1; s_next3 = 0; }
 
+    double maxpiv = 0.0;   // warp 0: largest pivot so far (uniform across its lanes)
     for (int k0 = 0; k0 < Lp; k0 += CH_NB) {
         const int nb = min(CH_NB, Lp - k0);   // multiple of 4
         const int rows = Ltot - k0;           // rows of the panel including its diagonal block
@@ -742,10 +743,13 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol(Dims d, cplx* __re
             __syncwarp();
             for (int c = 0; c < nb; ++c) {
                 double piv = sD[c * CH_DS + c].x;
-                if (!(piv > 0.0)) {
+                // numerically singular: non-positive, or below 1e-13 of the largest pivot so far (an exactly
+                // rank-deficient matrix leaves rounding noise of either sign here); identity padding exempt
+                if (!(piv > ((k0 + c < d.L) ? 1e-13 * maxpiv : 0.0))) {
                     if (r == 0) s_bad = 1;
                     piv = 1.0;
                 }
+                maxpiv = fmax(maxpiv, piv);
                 const double dg = sqrt(piv);
                 const double inv = 1.0 / dg;
                 __syncwarp();

@@ -44,6 +44,8 @@ class SweepConfig:
     legacy_rng: bool = True
     seed: int = 0
     max_batch: int = 4096         # trials per library call
+    on_device: bool = False       # generate inputs + LS start on the GPU (Philox; sbce_generate_batch / sbce_ls_start):
+                                  # nothing but the per-point accumulators crosses PCIe
 
 
 @dataclass
@@ -74,8 +76,54 @@ def _ser_as_coded_batch(Xd, Xest):
     return np.count_nonzero(diff, axis=(1, 2, 3)) / (Xd.shape[1] * Xd.shape[2])
 
 
+def run_point_device(cfg: SweepConfig, point_index: int, device=0, per_trial=None) -> PointResult:
+    """run_point with everything on the GPU: Philox generation straight into the SoA layout, LS start,
+    EM, NMSE / SER accumulation; one 6-double read-back per sweep point.  Trial b of the point is the
+    same whatever the batch size or the number of ranks (counter-based generator)."""
+    import torch
+
+    rank, ws = dist.world()
+    lo, hi = dist.shard_trials(cfg.monte_iter, rank, ws)
+    prob = engine.Problem(N=cfg.N, n_tx=cfg.n_tx, n_rx=cfg.n_rx, M=cfg.M, T_p=cfg.T_p, T_d=cfg.T_d, itera=cfg.itera,
+                          mode=cfg.mode, genie_stop=cfg.genie_stop, quirks=cfg.quirks,
+                          zero_start=(cfg.start == "zero"), partition_r=cfg.partition_r)
+    acc = PointResult()
+    if hi <= lo:
+        return acc
+    dev = torch.device("cuda", device)
+    pilot = "pm" if cfg.variant == "pm" else "top"
+    phases = "dft" if cfg.variant == "top_td" else "random"
+    with torch.cuda.device(dev):
+        nbmax = min(cfg.max_batch, hi - lo)
+        free, _ = torch.cuda.mem_get_info(dev)
+        per_trial_bytes = engine.workspace_bytes(prob, 1)
+        inflight = int(max(1, min(nbmax, (free // 3) // max(1, per_trial_bytes))))
+        ses = engine.DeviceSession(prob, inflight, device=dev)
+        acc_n = torch.zeros(3, dtype=torch.float64, device=dev)
+        acc_s = torch.zeros(3, dtype=torch.float64, device=dev)
+        for b0 in range(lo, hi, cfg.max_batch):
+            nb = min(cfg.max_batch, hi - b0)
+            tb = ses.generate(nb, cfg.varn, seed=cfg.seed * 1000003 + point_index, trial0=b0, pilot_design=pilot,
+                              data_phases=phases)
+            theta0, st0 = (None, None) if prob.zero_start else ses.ls_start(tb["Yp"], tb["PsiP"], tb["Xp"])
+            res = ses.run(tb["Yd"], tb["Yp"], tb["PsiD"], tb["PsiP"], tb["Xp"], tb["varn"], theta0=theta0,
+                          h_true=tb["h"])
+            if st0 is not None:
+                res.status.bitwise_or_(st0)   # a rank-deficient pilot block flags the trial
+            ses.accumulate(res, tb["Xd"], acc_n, acc_s if cfg.mode in ("soft", "hard", "zf", "mmse") else None)
+            if per_trial is not None:
+                per_trial[b0:b0 + nb] = res.nmse.cpu().numpy()
+            acc.n_trials += nb
+        a, c = acc_n.cpu().numpy(), acc_s.cpu().numpy()
+    acc.nmse_sum, acc.n_valid, acc.n_flagged = float(a[0]), float(a[1]), float(a[2])
+    acc.sym_err, acc.sym_total, acc.ser_coded_sum = float(c[0]), float(c[1]), float(c[2])
+    return acc
+
+
 def run_point(cfg: SweepConfig, point_index: int, runner: Callable = None, device=0, per_trial=None) -> PointResult:
     """All Monte-Carlo trials of one sweep point owned by this rank."""
+    if cfg.on_device and runner is None:
+        return run_point_device(cfg, point_index, device, per_trial)
     runner = runner or cuda_runner
     rank, ws = dist.world()
     lo, hi = dist.shard_trials(cfg.monte_iter, rank, ws)

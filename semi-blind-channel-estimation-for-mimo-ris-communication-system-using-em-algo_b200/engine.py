@@ -313,6 +313,64 @@ class DeviceSession:
         return theta, status
 
 
+    # ---- on-device generation + LS start (include/sbce.h: sbce_generate_batch, sbce_ls_start) ----
+    def generate(self, B, varn, seed, trial0=0, pilot_design="pm", data_phases="random", varh=1.0):
+        """Philox-generated trials written straight into device tensors (same names as
+        signal_model.TrialBatch: h, Xd, Xp, PsiP, PsiD, Yp, Yd, varn).  Trial b of the batch is global
+        trial trial0 + b of the sweep keyed by `seed`, independent of batch size and sharding."""
+        torch, p = self.torch, self.prob
+        dev = self.device
+        sh = p.shapes(B)
+        c128 = torch.complex128
+        tb = {k: torch.empty(sh[k], dtype=c128, device=dev) for k in ("Yd", "Yp", "PsiD", "PsiP", "Xp")}
+        tb["h"] = torch.empty(sh["h_true"], dtype=c128, device=dev)
+        tb["Xd"] = torch.empty(sh["Xd_true"], dtype=c128, device=dev)
+        if torch.is_tensor(varn):
+            tb["varn"] = varn.to(device=dev, dtype=torch.float64).expand(B).contiguous()
+        else:
+            tb["varn"] = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(np.asarray(varn, np.float64), (B,)))).to(dev)
+        io = _lib.Io()
+        io.Yd, io.Yp, io.PsiD, io.PsiP, io.Xp = (tb[k].data_ptr() for k in ("Yd", "Yp", "PsiD", "PsiP", "Xp"))
+        io.h_true, io.Xd_true, io.varn = tb["h"].data_ptr(), tb["Xd"].data_ptr(), tb["varn"].data_ptr()
+        g = _lib.Gen()
+        g.seed, g.trial0 = int(seed) & (2 ** 64 - 1), int(trial0)
+        g.pilot_design, g.data_phases, g.varh = _lib.PILOTS[pilot_design], _lib.PHASES_KIND[data_phases], float(varh)
+        cfg = p.cfg(B)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self.lib.sbce_generate_batch(C.byref(cfg), C.byref(g), C.byref(io), stream))
+        return tb
+
+    def ls_start(self, Yp, PsiP, Xp):
+        """h_initial = pinv(Z_p) y_p of every trial (PM.py:147) -> (theta0, status) device tensors."""
+        torch, p = self.torch, self.prob
+        B = int(Yp.shape[0])
+        dev = self.device
+        sh = p.shapes(B)
+        io = _lib.Io()
+        io.Yp = _t_ptr(self._check(Yp, sh["Yp"], "Yp", torch.complex128))
+        io.PsiP = _t_ptr(self._check(PsiP, sh["PsiP"], "PsiP", torch.complex128))
+        io.Xp = _t_ptr(self._check(Xp, sh["Xp"], "Xp", torch.complex128))
+        theta0 = torch.empty((B, p.L, p.n_rx), dtype=torch.complex128, device=dev)
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+        cfg = p.cfg(B)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self.lib.sbce_ls_start(C.byref(cfg), C.byref(io), theta0.data_ptr(), status.data_ptr(),
+                                          self.ws.data_ptr(), self.ws_bytes, stream))
+        return theta0, status
+
+    def accumulate(self, res: "Result", Xd, acc_nmse, acc_ser=None):
+        """Adds this batch to the per-point device accumulators: acc_nmse (3 float64: sum NMSE over valid
+        trials, valid count, flagged count), acc_ser (3 float64: symbol errors, symbols, sum of as-coded SER)."""
+        torch, p = self.torch, self.prob
+        B = int(res.theta.shape[0])
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.sbce_accumulate_nmse(res.nmse.data_ptr(), res.status.data_ptr(), B, acc_nmse.data_ptr(), stream))
+        if acc_ser is not None and res.kstar is not None and p.n_tx * int(math.log2(p.M)) <= 30:
+            cfg = p.cfg(B)
+            _lib.check(self.lib.sbce_accumulate_ser(C.byref(cfg), res.kstar.data_ptr(), Xd.data_ptr(), B,
+                                                    acc_ser.data_ptr(), stream))
+
+
 def fp64_peak_tflops():
     lib = _lib.require_device()
     tf, sec = C.c_double(0), C.c_double(0)
