@@ -391,6 +391,189 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_gram_mma4(Dims d, int T, cons
         }
 }
 
+// ---------------------------------------------------------------------------
+// k_gram_tma4: the same FP64 tensor-path Gram fed by the TMA engine.  The cp.async version above spends
+// only half of its warp time in the DMMA loop (profiles/r01h: 9 % issuing ~10 cp.async per thread and
+// chunk, 7 % at the two CTA barriers per chunk that couple all eight warps, 15 % in the epilogue).  The
+// staged operands are CONTIGUOUS in global memory -- 16 symbols of psi ([16][N+1] complex) and of R_t
+// ([16][16] complex) -- so one elected lane of a producer warp moves each chunk with two 1-D bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx) into a 4-stage ring; the eight DMMA warps never touch the
+// staging: each waits on the stage's `full` mbarrier, runs its DMMAs and arrives on `empty` on its own
+// -- no __syncthreads in the loop, so a slow warp no longer stalls the other seven.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int GT_TC = 16;        // symbols per stage
+constexpr int GT_STAGES = 4;     // ring depth
+constexpr int GT_THREADS = GR_THREADS;        // 8 DMMA warps; warp 0's elected lane also drives the TMA ring
+
+__global__ void __launch_bounds__(GT_THREADS, 2) k_gram_tma4(Dims d, int T, const cplx* __restrict__ Psi,
+                                                            const cplx* __restrict__ sR, const cplx* __restrict__ Y,
+                                                            const cplx* __restrict__ sm, const cplx* __restrict__ Ginit,
+                                                            cplx* __restrict__ Gout, const int32_t* __restrict__ active) {
+    constexpr int NTX = 4;
+    extern __shared__ __align__(128) double2 gsm[];
+    __shared__ __align__(8) unsigned long long bar_full[GT_STAGES], bar_empty[GT_STAGES];
+    const int b = blockIdx.y;
+    if (active != nullptr && active[b] == 0) return;
+    const int N1 = d.N1;
+    const int P = N1 * (N1 + 1) / 2;
+    const cplx* psi_b = Psi + (size_t)(d.psi_shared ? 0 : b) * T * N1;
+    const size_t gstride = (size_t)d.Ltot * d.Lp;
+    cplx* Gb = Gout + (size_t)b * gstride;
+    const cplx* Gi = Ginit ? Ginit + (size_t)b * gstride : nullptr;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    if (blockIdx.x == gridDim.x - 1) {
+        gram_rhs_cta<NTX>(d, T, b, gsm, gsm + GR_TC * N1, psi_b, Y, sm, Gi, Gb);
+        return;
+    }
+    const int stage_elems = GT_TC * (N1 + NTX * NTX);   // complex elements per stage: [TC][N1] psi, [TC][16] R
+    const cplx* R_b = sR + (size_t)b * T * NTX * NTX;
+    const int nchunk = (T + GT_TC - 1) / GT_TC;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], GR_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // producer: fills stage (ck % STAGES) with chunk ck; executed by warp 0 (all lanes for the ragged
+    // zero fill, the elected lane for the barrier and the two bulk copies)
+    auto produce = [&](int ck) {
+        const int s = ck % GT_STAGES;
+        const int t0 = ck * GT_TC;
+        const int tc = min(GT_TC, T - t0);
+        cplx* dpsi = gsm + s * stage_elems;
+        cplx* dR = dpsi + GT_TC * N1;
+        if (tc < GT_TC) {   // ragged last chunk: symbols beyond T contribute zero
+            for (int e = tc * N1 + lane; e < GT_TC * N1; e += 32) dpsi[e] = mk(0.0, 0.0);
+            for (int e = tc * NTX * NTX + lane; e < GT_TC * NTX * NTX; e += 32) dR[e] = mk(0.0, 0.0);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            const unsigned bpsi = (unsigned)(tc * N1 * sizeof(cplx)), bR = (unsigned)(tc * NTX * NTX * sizeof(cplx));
+            mbar_expect_tx(&bar_full[s], bpsi + bR);
+            tma_bulk_g2s(dpsi, psi_b + (size_t)t0 * N1, bpsi, &bar_full[s]);
+            tma_bulk_g2s(dR, R_b + (size_t)t0 * NTX * NTX, bR, &bar_full[s]);
+        }
+        __syncwarp();
+    };
+    if (warp == 0)
+        for (int ck = 0; ck < min(GT_STAGES, nchunk); ++ck) produce(ck);
+
+    // ---------------- DMMA warps: pairs of this lane: tile u (0,1), row half h (0,1) -> item
+    int pn[2][2], pnp[2][2];
+    bool pv[2][2], tile_live[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        tile_live[u] = (blockIdx.x * GR_THREADS + (2 * warp + u) * 16) < P;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int item = blockIdx.x * GR_THREADS + (2 * warp + u) * 16 + g + 8 * h;
+            pv[u][h] = item < P;
+            item = min(item, P - 1);
+            int n = (int)((sqrt(8.0 * item + 1.0) - 1.0) * 0.5);
+            while ((n + 1) * (n + 2) / 2 <= item) ++n;
+            while (n * (n + 1) / 2 > item) --n;
+            pn[u][h] = n;
+            pnp[u][h] = item - n * (n + 1) / 2;
+        }
+    }
+    const int boff0 = gram_bcol_offset(g), boff1 = gram_bcol_offset(8 + g);
+    double accr[2][2][4], acci[2][2][4];  // [tile][n-tile][c0..c3]
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { accr[u][nt][e] = 0.0; acci[u][nt][e] = 0.0; }
+
+    for (int ck = 0; ck < nchunk; ++ck) {
+        const int s = ck % GT_STAGES;
+        // refill the stage of the PREVIOUS chunk (three chunks of look-ahead): by now the other warps have
+        // almost always released it, so the wait on its `empty` barrier rarely blocks warp 0
+        if (warp == 0 && ck >= 1 && ck - 1 + GT_STAGES < nchunk) {
+            mbar_wait(&bar_empty[(ck - 1) % GT_STAGES], ((ck - 1) / GT_STAGES) & 1);
+            produce(ck - 1 + GT_STAGES);
+        }
+        mbar_wait(&bar_full[s], (ck / GT_STAGES) & 1);
+        const cplx* cPsi = gsm + s * stage_elems;
+        const double* cR = (const double*)(cPsi + GT_TC * N1);
+#pragma unroll
+        for (int ks = 0; ks < GT_TC / 8; ++ks) {
+            const int tlo = ks * 8 + tig, thi = tlo + 4;
+            const double b00 = cR[tlo * 32 + boff0], b01 = cR[thi * 32 + boff0];
+            const double b10 = cR[tlo * 32 + boff1], b11 = cR[thi * 32 + boff1];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!tile_live[u]) continue;   // warp-uniform: ragged last pair CTA of a trial
+                // A fragment order: (row g, t lo), (row g+8, t lo), (row g, t hi), (row g+8, t hi)
+                const cplx p0 = cmulc(cPsi[tlo * N1 + pnp[u][0]], cPsi[tlo * N1 + pn[u][0]]);
+                const cplx p1 = cmulc(cPsi[tlo * N1 + pnp[u][1]], cPsi[tlo * N1 + pn[u][1]]);
+                const cplx p2 = cmulc(cPsi[thi * N1 + pnp[u][0]], cPsi[thi * N1 + pn[u][0]]);
+                const cplx p3 = cmulc(cPsi[thi * N1 + pnp[u][1]], cPsi[thi * N1 + pn[u][1]]);
+                const double pr[4] = {p0.x, p1.x, p2.x, p3.x};
+                const double pi[4] = {p0.y, p1.y, p2.y, p3.y};
+                dmma16x8x8(accr[u][0], pr, b00, b01);
+                dmma16x8x8(accr[u][1], pr, b10, b11);
+                dmma16x8x8(acci[u][0], pi, b00, b01);
+                dmma16x8x8(acci[u][1], pi, b10, b11);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[s]);   // this warp is done with the stage
+    }
+    // epilogue: accumulator (row g + 8h, cols 2 tig, 2 tig + 1 of n-tile nt)
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (!pv[u][h]) continue;
+            const int n = pn[u][h], np = pnp[u][h];
+            auto put = [&](int i, int j, cplx v) {
+                const size_t o = (size_t)(n * NTX + i) * d.Lp + (np * NTX + j);
+                if (Gi) v = cadd(v, Gi[o]);
+                Gb[o] = v;
+            };
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const double r0 = accr[u][nt][2 * h], r1 = accr[u][nt][2 * h + 1];
+                const double i0 = acci[u][nt][2 * h], i1 = acci[u][nt][2 * h + 1];
+                const int col = 8 * nt + 2 * tig;
+                if (col < 4) {  // two diagonal entries: (pr Rd, pi Rd)
+                    put(col, col, mk(r0, i0));
+                    put(col + 1, col + 1, mk(r1, i1));
+                } else {        // one upper pair q: U = pr Rr, W = pr Ri, Z = pi Rr, V = pi Ri
+                    const int q = (col - 4) >> 1;
+                    const int qi = (q < 3) ? 0 : (q < 5 ? 1 : 2);
+                    const int qj = (q < 3) ? q + 1 : (q < 5 ? q - 1 : 3);
+                    put(qi, qj, mk(r0 - i1, r1 + i0));
+                    put(qj, qi, mk(r0 + i1, i0 - r1));
+                }
+            }
+        }
+}
+
 // Generic tensor-path Gram, n_tx = 4..8.  Column layout of the real B matrix (NC columns, padded to a
 // multiple of 8): [0, NTX) the real diagonal of R_t; from the even offset PO on, (re, im) of the upper
 // entries (i<j) in row-major order.  A warp owns one 16-pair tile and all NT column tiles; the chunk
@@ -585,6 +768,23 @@ static cudaError_t run_gram(const Dims& d, int nb, const double* Psi, int T, con
     }
     if (NTX == 4 && use_mma && sizeof(cplx) * (size_t)(2 * GM_TC * (d.N1 + NTX * NTX)) > 160 * 1024)
         return run_gram_wide<4>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
+    static int use_tma = -1;
+    if (use_tma < 0) {
+        const char* v = getenv("SBCE_GRAM_TMA");
+        use_tma = (v && !atoi(v)) ? 0 : 1;
+    }
+    if (NTX == 4 && use_mma && use_tma) {
+        size_t smem_tma = sizeof(cplx) * (size_t)(GT_STAGES * GT_TC * (d.N1 + NTX * NTX));
+        if (smem_rhs > smem_tma) smem_tma = smem_rhs;
+        if (smem_tma > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_gram_tma4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
+            if (e != cudaSuccess) return e;
+        }
+        k_gram_tma4<<<grid, GT_THREADS, smem_tma, s>>>(d, T, (const cplx*)Psi, (const cplx*)sR, (const cplx*)Y,
+                                                       (const cplx*)sm, (const cplx*)Ginit, (cplx*)Gout, active);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (NTX == 4 && use_mma) {
         const size_t smem_mma = sizeof(cplx) * (size_t)(2 * GM_TC * (d.N1 + NTX * NTX));
         if (smem_mma > smem) smem = smem_mma;
