@@ -345,18 +345,19 @@ def run_ours(args):
             k["frac_hbm_peak"] = k["gbs"] / hbm_peak
         kernels[name] = k
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-    # (profiles/r01e_top_kernels_full.csv), valid for the default workload at 592 trials per launch
-    ncu_traffic = {"chol": 2.268065e9 + 528.896512e6, "gram": 0.562659e9 + 312.172288e6,
-                   "heff_qr": 0.177387e9 + 17.866240e6, "enum": 0.036421e9 + 7.767040e6}
+    # (profiles/r01k_top_kernels_full.csv), valid for the default workload at 592 trials per launch
+    ncu_traffic = {"chol": 2.382261e9 + 590.672128e6, "gram": 0.578337e9 + 312.873984e6,
+                   "heff_qr": 0.177411e9 + 18.087168e6, "enum": 0.036424e9 + 8.273408e6}
     top = max((n for n in kernels if n in fm), key=lambda n: kernels[n]["ms_total"])
-    roofline = dict(bound="fp64", kernel=top, achieved=kernels[top]["tflops"], peak=fp64_peak, unit="TFLOP/s",
+    roofline = dict(bound="tensor", pipe="FP64 tensor path (mma.sync DMMA; tcgen05 has no FP64 kind)", kernel=top, achieved=kernels[top]["tflops"], peak=fp64_peak, unit="TFLOP/s",
                     frac=kernels[top]["frac_fp64_peak"],
                     traffic=(ncu_traffic.get(top) if (B == 592 and w == WORKLOAD) else None),
-                    traffic_unit="bytes per launch (ncu dram read+write, profiles/r01e_top_kernels_full.csv)",
+                    traffic_unit="bytes per launch (ncu dram read+write, profiles/r01k_top_kernels_full.csv)",
                     share_of_step=kernels[top]["share"],
                     peak_source="live DFMA micro-benchmark in libsbce (2 flop/FMA); MEASURED_PEAKS.json has no FP64 entry",
                     flops_per_launch=fm[top] * B,
-                    note="FP64 vector pipe bound (tcgen05 has no FP64 kind); algorithmic flop models in DESIGN.md section 5")
+                    note="peak = measured FP64 rate (DFMA and DMMA m16n8k8 both 37 TFLOP/s on this B200, "
+                         "tools/microbench); executed-flop models in DESIGN.md section 5")
     if "heff_qr" in kernels and "gbs" in kernels["heff_qr"]:
         roofline["hbm_side"] = dict(kernel="heff_qr", achieved=kernels["heff_qr"]["gbs"], peak=hbm_peak, unit="GB/s",
                                     frac=kernels["heff_qr"]["frac_hbm_peak"], peak_source=hbm_src)
