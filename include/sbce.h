@@ -64,6 +64,11 @@ extern "C" {
                                    they could neither improve the arg-min nor enter the posterior sums, so the
                                    outputs are BIT-IDENTICAL to the full scan (tests/test_gpu_parity.py)              */
 
+#define SBCE_FLAG_SUPERIMPOSED 32u /* parallel protocol (/root/reference/Parallel/ParallelProtocol_Tp.py:64-86): pilots are
+                                   SUPERIMPOSED on the data, the hypotheses of symbol t are x_k + o_t with the known offset
+                                   o_t (pilot symbol, zero beyond the pilot length), there is no separate pilot block:
+                                   T_p must be 0 and io->Xp holds the offsets [B][T_d][n_tx]; soft / hard modes only */
+
 /* per-trial status bits */
 #define SBCE_ST_NOT_PD 1    /* non-positive pivot in the Cholesky of the normal matrix (singular M-step) */
 #define SBCE_ST_NONFINITE 2 /* a non-finite value appeared in theta                                      */
@@ -95,7 +100,7 @@ typedef struct sbce_io {
     const double* Yp;      /* [B][T_p][n_rx]                                                   */
     const double* PsiD;    /* [B][T_d][N+1]  (or [T_d][N+1] with SBCE_FLAG_PSI_SHARED)          */
     const double* PsiP;    /* [B][T_p][N+1]  (or [T_p][N+1])                                   */
-    const double* Xp;      /* [B][T_p][n_tx] pilot symbols                                     */
+    const double* Xp;      /* [B][T_p][n_tx] pilot symbols  ([B][T_d][n_tx] offsets with SBCE_FLAG_SUPERIMPOSED) */
     const double* theta0;  /* [B][L][n_rx]   start point; nullable with SBCE_FLAG_ZERO_START   */
     const double* varn;    /* [B] float64 -- the E-step divides by varn^2 (reference quirk Q1) */
     const double* h_true;  /* [B][L][n_rx]   nullable: needed for nmse[] and the genie stop    */
@@ -171,7 +176,9 @@ typedef struct sbce_gen {
     int32_t pilot_design; /* SBCE_PILOTS_*                                                     */
     int32_t data_phases;  /* SBCE_PHASES_*                                                     */
     double varh;          /* channel variance (reference: 1)                                   */
-    int32_t reserved[4];
+    int32_t no_direct_link; /* 1: every one of the cfg->N + 1 phase rows is a RIS element (no ones row, no H_BU):
+                               "Proposed method/direct vs non direct - T_pv s nmse.py":11-18,108-120               */
+    int32_t reserved[3];
 } sbce_gen;
 
 /* Fills the caller's DEVICE buffers io->h_true, Xp, Xd_true, PsiP, PsiD, Yp, Yd (declared const in

@@ -357,6 +357,32 @@ def em(Yd, Yp, PsiD, PsiP, Xp, M, varn, itera, theta0=None, n_tx=None, hard=Fals
     return (Theta, trace) if return_trace else Theta
 
 
+def em_superimposed(Y, Psi, Xoff, M, varn, itera, n_tx=None, hard=False, return_trace=False):
+    """Parallel protocol, `Parallel/ParallelProtocol_Tp.py:64-86`: pilots are superimposed on the data,
+    the hypotheses of symbol t are x_k + o_t (o_t = pilot symbol, zero beyond the pilot length, :56-62),
+    there is no separate pilot term and theta starts at 0.  With x~ = x + o:
+        d2_k = ||(y - Heff o) - Heff x_k||^2,  m~ = m + conj(o),
+        R~_ij = R_ij + m_i o_j + conj(o_i) conj(m_j) + conj(o_i) o_j."""
+    n_tx = Xoff.shape[1] if n_tx is None else n_tx
+    L, n_rx = Psi.shape[1] * n_tx, Y.shape[1]
+    cons = qam_constellation(M)
+    Theta = np.zeros((L, n_rx), dtype=np.complex128)
+    trace = dict(kstar=None, lse=[], iters=0)
+    for l in range(itera):
+        Heff = effective_channels(Psi, Theta, n_tx)
+        Yshift = Y - np.einsum("trj,tj->tr", Heff, Xoff)
+        m, R, kstar, lse = posterior_stats(Yshift, Psi, Theta, cons, n_tx, varn, hard=hard)
+        Rt = (R + m[:, :, None] * Xoff[:, None, :] + Xoff.conj()[:, :, None] * m.conj()[:, None, :]
+              + Xoff.conj()[:, :, None] * Xoff[:, None, :])
+        mt = m + Xoff.conj()
+        G, B = gram_and_rhs(Psi, Y, mt, Rt)
+        Theta = solve_normal(G, B)
+        trace["kstar"] = kstar
+        trace["lse"].append(float(lse.sum()))
+        trace["iters"] = l + 1
+    return (Theta, trace) if return_trace else Theta
+
+
 def _argmax_complex_first(v):
     """np.argmax on a complex vector orders lexicographically (real, then imag),
     first index on ties (`Proposed method/PM.py:67`)."""

@@ -108,6 +108,61 @@ def case_soft_top(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn):
     _save(name, meta, d)
 
 
+def case_nodirect(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn):
+    """No-direct-link layout: `Proposed method/direct vs non direct - T_pv s nmse.py`, both of its
+    estimators on the driver's own data (:159-171): `em` (:82-106; N phase rows, L = N n_tx, zero start) and
+    `em_direct_in` (:45-80; ones row inserted, L = (N+1) n_tx)."""
+    ns = rh.load_functions("Proposed method/direct vs non direct - T_pv s nmse.py")
+    np.random.seed(seed)
+    with rh.quiet():
+        h_direct_in, h = ns["channelMatrix"](n_tx, n_rx, N, 1)
+        X_d, aps = ns["symbols"](n_tx, M, T_d)
+        PsiTilde_tp, PsiTilde_td = ns["irsMatrix"](T_p, T_d, N, 0, 1)
+        X_p = ns["pilotSymbols"](n_tx, M, T_p)
+        Y_p, Y_d, Z_p, Z_d = ns["receivedSignals"](T_p, T_d, PsiTilde_tp, PsiTilde_td, n_rx, n_tx, X_d, X_p, h, varn, M)
+        theta = ns["em"](Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, aps, M, varn, itera, n_tx, N)
+        Pp1 = np.insert(PsiTilde_tp, 0, np.ones((1, T_p), dtype="complex128"), axis=0)
+        Pd1 = np.insert(PsiTilde_td, 0, np.ones((1, T_d), dtype="complex128"), axis=0)
+        Y_p1, Y_d1, Z_p1, Z_d1 = ns["receivedSignals"](T_p, T_d, Pp1, Pd1, n_rx, n_tx, X_d, X_p, h_direct_in, varn, M)
+        theta1 = ns["em_direct_in"](Y_d1, Y_p1, T_d, T_p, Z_p1, Pd1, aps, M, varn, itera, N, n_tx)
+    d = rh.extract_arrays(Y_p, Y_d, Z_p, X_p, X_d, PsiTilde_tp, PsiTilde_td, h, None, n_tx, n_rx)
+    d1 = rh.extract_arrays(Y_p1, Y_d1, Z_p1, X_p, X_d, Pp1, Pd1, h_direct_in, None, n_tx, n_rx)
+    meta = dict(kind="nodirect", seed=seed, N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera, varn=varn,
+                src="Proposed method/direct vs non direct - T_pv s nmse.py:em,em_direct_in", zero_start=1, h_order="C")
+    d.update(theta_ref=np.asarray(theta, dtype=np.complex128).reshape(N * n_tx, n_rx), nmse_ref=_nmse(theta, h))
+    for k, v in d1.items():
+        if v is not None:
+            d["din_" + k] = v
+    d.update(din_theta_ref=np.asarray(theta1, dtype=np.complex128).reshape((N + 1) * n_tx, n_rx),
+             din_nmse_ref=_nmse(theta1, h_direct_in))
+    _save(name, meta, d)
+
+
+def case_parallel(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn):
+    """Superimposed pilots: `Parallel/ParallelProtocol_Tp.py` em (:64-86) on the driver's own data
+    (:119-128): channel, symbols, then per point irsMatrix, pilotSymbols, dataPilotSymbols, receivedSignals."""
+    ns = rh.load_functions("Parallel/ParallelProtocol_Tp.py")
+    np.random.seed(seed)
+    with rh.quiet():
+        h = ns["channelMatrix"](n_tx, n_rx, N, 1)
+        X_d, aps = ns["symbols"](n_tx, M, T_d)
+        T = max(T_d, T_p)
+        PsiTilde_t = ns["irsMatrix"](T, N)
+        X_p = ns["pilotSymbols"](n_tx, M, T_p)
+        X = ns["dataPilotSymbols"](n_tx, X_p, X_d)
+        Y, Z = ns["receivedSignals"](T, PsiTilde_t, n_rx, n_tx, X, h, varn)
+        theta = ns["em"](Y, T, Z, X_d, X_p, T_p, T_d, n_tx, PsiTilde_t, aps, M, varn, itera, N)
+    Xoff = np.zeros((T, n_tx), dtype=np.complex128)
+    Xoff[:T_p] = np.hstack(X_p).T
+    L = (N + 1) * n_tx
+    meta = dict(kind="parallel", seed=seed, N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, T=T, itera=itera, varn=varn,
+                src="Parallel/ParallelProtocol_Tp.py:em", zero_start=1, h_order="C")
+    d = dict(Y=np.hstack(Y).T.copy(), Psi=np.asarray(PsiTilde_t).T.copy(), Xoff=Xoff, Xp=np.hstack(X_p).T.copy(),
+             Xd=np.hstack(X_d).T.copy(), h=np.asarray(h).reshape(L, n_rx).copy(),
+             theta_ref=np.asarray(theta, dtype=np.complex128).reshape(L, n_rx), nmse_ref=_nmse(theta, h))
+    _save(name, meta, d)
+
+
 def case_hard_llf(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn):
     """Hard EM + as-coded LLF: `Proposed method/ML_detecctor.py:51-86`."""
     ns = rh.load_functions("Proposed method/ML_detecctor.py", N=N, n_tx=n_tx, n_rx=n_rx, beta_max=TWO_PI)
@@ -285,6 +340,14 @@ def main(argv):
         case_detectors("det_3x3_s32", 32, 5, 3, 3, 4, 5, 20, 4, 0.5)
     if want("det_2x4_s33"):
         case_detectors("det_2x4_s33", 33, 7, 2, 4, 4, 7, 30, 5, 1.0)
+    if want("nodirect_s41"):
+        case_nodirect("nodirect_s41", 41, 6, 2, 2, 4, 10, 20, 3, 0.1)
+    if want("nodirect_1x4_s42"):
+        case_nodirect("nodirect_1x4_s42", 42, 8, 1, 4, 16, 12, 24, 3, 0.2)
+    if want("parallel_1x4_s51"):
+        case_parallel("parallel_1x4_s51", 51, 5, 1, 4, 16, 8, 24, 4, 0.1)
+    if want("parallel_2x2_s52"):
+        case_parallel("parallel_2x2_s52", 52, 4, 2, 2, 4, 30, 20, 3, 0.2)
     if want("script_top_td_s0"):
         case_script("script_top_td_s0", "Proposed_method_NMSEvsTd.py", 0)
     if want("script_top_tp_s0"):

@@ -61,11 +61,15 @@ def _dft(T, ns, denom):
     return np.exp(-2j * np.pi * q / denom)
 
 
-def generate_trial(N, n_tx, n_rx, M, T_p, T_d, varn, seed, trial, pilot_design="pm", data_phases="random", varh=1.0):
+def generate_trial(N, n_tx, n_rx, M, T_p, T_d, varn, seed, trial, pilot_design="pm", data_phases="random", varh=1.0,
+                   direct_link=True):
     """One trial exactly as csrc/gen.cu generates it.  Returns a dict with the estimator layout of
-    oracle/em_numpy.py plus the symbol indices and the noise blocks."""
+    oracle/em_numpy.py plus the symbol indices and the noise blocks.  N + 1 phase rows; with
+    direct_link=False all of them are RIS elements ("direct vs non direct - T_pv s nmse.py")."""
     s = int(round(M ** 0.5))
     hb = (M.bit_length() - 1) // 2
+    if not direct_link:
+        return _generate_trial_nodirect(N + 1, n_tx, n_rx, M, T_p, T_d, varn, seed, trial, pilot_design, data_phases, varh)
     H_BU = _cn(seed, 0, trial, np.arange(n_rx * n_tx), varh).reshape(n_rx, n_tx)
     H_BS = _cn(seed, 1, trial, np.arange(N * n_tx), varh).reshape(N, n_tx)
     H_SU = _cn(seed, 2, trial, np.arange(n_rx * N), varh).reshape(n_rx, N)
@@ -92,6 +96,34 @@ def generate_trial(N, n_tx, n_rx, M, T_p, T_d, varn, seed, trial, pilot_design="
         x, y, _, _ = _draw(seed, 5, trial, np.arange(T_d * N))
         PsiD = np.ones((T_d, N + 1), np.complex128)
         PsiD[:, 1:] = np.exp(2j * np.pi * _u53(x, y)).reshape(T_d, N)
+    noise_p = _cn(seed, 6, trial, np.arange(T_p * n_rx), varn).reshape(T_p, n_rx)
+    noise_d = _cn(seed, 7, trial, np.arange(T_d * n_rx), varn).reshape(T_d, n_rx)
+    Wp = (PsiP[:, :, None] * Xp[:, None, :]).reshape(T_p, -1)
+    Wd = (PsiD[:, :, None] * Xd[:, None, :]).reshape(T_d, -1)
+    return dict(h=h, Xp=Xp.astype(np.complex128), Xd=Xd.astype(np.complex128), idx_p=idx_p, idx_d=idx_d, PsiP=PsiP,
+                PsiD=PsiD, Yp=Wp @ h + noise_p, Yd=Wd @ h + noise_d, noise_p=noise_p, noise_d=noise_d, Wp=Wp)
+
+
+def _generate_trial_nodirect(R, n_tx, n_rx, M, T_p, T_d, varn, seed, trial, pilot_design, data_phases, varh):
+    """R RIS elements, no BS-user link: Theta[n][j][r] = H_BS[n, j] H_SU[r, n]; every phase row is an element."""
+    s = int(round(M ** 0.5))
+    hb = (M.bit_length() - 1) // 2
+    H_BS = _cn(seed, 1, trial, np.arange(R * n_tx), varh).reshape(R, n_tx)
+    H_SU = _cn(seed, 2, trial, np.arange(n_rx * R), varh).reshape(n_rx, R)
+    h = (H_BS[:, :, None] * H_SU.T[:, None, :]).reshape(R * n_tx, n_rx)
+
+    def syms(stream, T):
+        idx = (_draw(seed, stream, trial, np.arange(T * n_tx))[0] & np.uint64(M - 1)).astype(np.int64).reshape(T, n_tx)
+        return idx, (2 * (idx & (s - 1)) - s + 1) + 1j * (2 * (idx >> hb) - s + 1)
+
+    idx_d, Xd = syms(3, T_d)
+    idx_p, Xp = syms(4, T_p)
+    PsiP = _dft(T_p, np.arange(R), R if pilot_design == "pm" else T_p)
+    if data_phases == "dft":
+        PsiD = _dft(T_d, np.arange(R), T_d)
+    else:
+        x, y, _, _ = _draw(seed, 5, trial, np.arange(T_d * R))
+        PsiD = np.exp(2j * np.pi * _u53(x, y)).reshape(T_d, R)
     noise_p = _cn(seed, 6, trial, np.arange(T_p * n_rx), varn).reshape(T_p, n_rx)
     noise_d = _cn(seed, 7, trial, np.arange(T_d * n_rx), varn).reshape(T_d, n_rx)
     Wp = (PsiP[:, :, None] * Xp[:, None, :]).reshape(T_p, -1)

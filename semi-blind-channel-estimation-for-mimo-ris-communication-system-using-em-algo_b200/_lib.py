@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsbce.so")
 
 MODE_SOFT, MODE_HARD, MODE_PM, MODE_PM_BETA, MODE_ZF, MODE_MMSE = 0, 1, 2, 3, 4, 5
-FLAG_GENIE_STOP, FLAG_QUIRKS, FLAG_PSI_SHARED, FLAG_ZERO_START, FLAG_FULL_SCAN = 1, 2, 4, 8, 16
+FLAG_GENIE_STOP, FLAG_QUIRKS, FLAG_PSI_SHARED, FLAG_ZERO_START, FLAG_FULL_SCAN, FLAG_SUPERIMPOSED = 1, 2, 4, 8, 16, 32
 ST_NOT_PD, ST_NONFINITE = 1, 2
 
 
@@ -38,7 +38,7 @@ class Io(C.Structure):
 
 class Gen(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("trial0", C.c_int64), ("pilot_design", C.c_int32), ("data_phases", C.c_int32),
-                ("varh", C.c_double), ("reserved", C.c_int32 * 4)]
+                ("varh", C.c_double), ("no_direct_link", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 PILOTS = {"pm": 0, "top": 1, "top_tp": 1, "top_td": 1}

@@ -70,6 +70,10 @@ static int make_dims(const sbce_cfg* c, Dims* d, bool with_estep = true) {
         if (c->partition_p1 < 1 || c->partition_p1 > c->n_tx) return SBCE_E_SHAPE;
     }
     if (c->mode >= SBCE_MODE_PM && c->n_rx < c->n_tx) return SBCE_E_UNSUPPORTED;
+    if (c->flags & SBCE_FLAG_SUPERIMPOSED) {
+        if (c->T_p != 0) return SBCE_E_SHAPE;
+        if (c->mode != SBCE_MODE_SOFT && c->mode != SBCE_MODE_HARD) return SBCE_E_UNSUPPORTED;
+    }
     return 0;
 }
 
@@ -112,15 +116,16 @@ cudaError_t launch_pm_stats(const Dims& d, int nb, const double* Yd, const doubl
 
 static int estep_dispatch(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
                           const double* varn, const int32_t* active, Workspace& ws, double* stat_m, double* stat_R,
-                          int32_t* kstar, double* lse_sym, cudaStream_t s) {
+                          int32_t* kstar, double* lse_sym, const double* Xoff, cudaStream_t s) {
     if (d.mode == SBCE_MODE_SOFT || d.mode == SBCE_MODE_HARD) {
         {
             PhaseScope ps(SBCE_PHASE_HEFF_QR, s);
-            CK(launch_heff_qr(d, nb, Yd, PsiD, theta, active, ws.qr, s));
+            CK(launch_heff_qr(d, nb, Yd, PsiD, theta, active, Xoff, ws.qr, s));
         }
         {
             PhaseScope ps(SBCE_PHASE_ENUM, s);
             CK(launch_enum(d, nb, ws.qr, varn, active, stat_m, stat_R, kstar, lse_sym, s));
+            if (Xoff) CK(launch_superimpose_stats(d, nb, Xoff, active, stat_m, stat_R, s));
         }
     } else {
         PhaseScope ps(SBCE_PHASE_ENUM, s);
@@ -140,7 +145,7 @@ static int em_chunk(const Dims& d, int nb, const sbce_io& io, Workspace& ws, cud
     }
     for (int l = 0; l < d.itera; ++l) {
         int rc = estep_dispatch(d, nb, io.Yd, io.PsiD, io.theta, io.varn, ws.active, ws, ws.stat_m, ws.stat_R,
-                                io.kstar, ws.lse_sym, s);
+                                io.kstar, ws.lse_sym, (d.flags & SBCE_FLAG_SUPERIMPOSED) ? io.Xp : nullptr, s);
         if (rc) return rc;
         {
             PhaseScope ps(SBCE_PHASE_GRAM, s);
@@ -175,7 +180,7 @@ static sbce_io offset_io(const Dims& d, const sbce_io& io, size_t b0) {
         o.PsiD = adv(io.PsiD, b0 * d.T_d * d.N1 * 2);
         o.PsiP = adv(io.PsiP, b0 * d.T_p * d.N1 * 2);
     }
-    o.Xp = adv(io.Xp, b0 * d.T_p * d.n_tx * 2);
+    o.Xp = adv(io.Xp, b0 * ((d.flags & SBCE_FLAG_SUPERIMPOSED) ? d.T_d : d.T_p) * d.n_tx * 2);
     o.theta0 = adv(io.theta0, b0 * Ln);
     o.varn = adv(io.varn, b0);
     o.h_true = adv(io.h_true, b0 * Ln);
@@ -196,6 +201,7 @@ static int check_io(const Dims& d, const sbce_io* io) {
     if (d.T_p > 0 && (!io->Yp || !io->PsiP || !io->Xp)) return SBCE_E_NULL;
     if (!(d.flags & SBCE_FLAG_ZERO_START) && !io->theta0) return SBCE_E_NULL;
     if ((d.flags & SBCE_FLAG_GENIE_STOP) && !io->h_true) return SBCE_E_NULL;
+    if ((d.flags & SBCE_FLAG_SUPERIMPOSED) && !io->Xp) return SBCE_E_NULL;
     return 0;
 }
 
@@ -287,7 +293,7 @@ int sbce_estep(const sbce_cfg* cfg, const sbce_io* io, const double* theta, doub
         const size_t sb = (size_t)b0 * d.T_d;
         rc = estep_dispatch(d, nb, o.Yd, o.PsiD, theta + (size_t)b0 * d.L * d.n_rx * 2, o.varn, nullptr, ws,
                             stat_m + sb * d.n_tx * 2, stat_R + sb * d.n_tx * d.n_tx * 2, kstar ? kstar + sb : nullptr,
-                            lse_sym ? lse_sym + sb : nullptr, s);
+                            lse_sym ? lse_sym + sb : nullptr, (d.flags & SBCE_FLAG_SUPERIMPOSED) ? o.Xp : nullptr, s);
         if (rc) return rc;
     }
     return 0;
@@ -472,7 +478,8 @@ int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device) {
     Seg sYp = seg(io->Yp, B * d.T_p * d.n_rx * 16, true, nullptr);
     Seg sPd = seg(io->PsiD, psiB * d.T_d * d.N1 * 16, true, nullptr);
     Seg sPp = seg(io->PsiP, psiB * d.T_p * d.N1 * 16, true, nullptr);
-    Seg sXp = seg(io->Xp, B * d.T_p * d.n_tx * 16, true, nullptr);
+    const size_t xpT = (d.flags & SBCE_FLAG_SUPERIMPOSED) ? d.T_d : d.T_p;   // offsets ride in Xp
+    Seg sXp = seg(io->Xp, B * xpT * d.n_tx * 16, true, nullptr);
     Seg sT0 = seg(io->theta0, B * Ln, true, nullptr);
     Seg sVn = seg(io->varn, B * 8, true, nullptr);
     Seg sHt = seg(io->h_true, B * Ln, true, nullptr);
@@ -514,7 +521,7 @@ int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device) {
     struct Part { Seg* q; size_t per_trial; };
     Part ins[] = {{&sYd, (size_t)d.T_d * d.n_rx * 16}, {&sYp, (size_t)d.T_p * d.n_rx * 16},
                   {&sPd, d.psi_shared ? 0 : (size_t)d.T_d * d.N1 * 16}, {&sPp, d.psi_shared ? 0 : (size_t)d.T_p * d.N1 * 16},
-                  {&sXp, (size_t)d.T_p * d.n_tx * 16}, {&sT0, Ln}, {&sVn, 8}, {&sHt, Ln},
+                  {&sXp, xpT * d.n_tx * 16}, {&sT0, Ln}, {&sVn, 8}, {&sHt, Ln},
                   {&sXd, (size_t)d.T_d * d.n_tx * 16}};
     Part outs[] = {{&oTh, Ln}, {&oKs, (size_t)d.T_d * 4}, {&oLl, (size_t)d.itera * 8}, {&oLs, (size_t)d.itera * 8},
                    {&oNm, 8}, {&oIt, 4}, {&oSt, 4}};

@@ -99,7 +99,9 @@ size_t carve_workspace(const Dims& d, int nb, void* base, Workspace* ws);
 // E-step side (estep.cu)
 cudaError_t launch_pilot_stats(const Dims& d, int nb, const double* Xp, double* pil_m, double* pil_R, cudaStream_t s);
 cudaError_t launch_heff_qr(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
-                           const int32_t* active, double* qr, cudaStream_t s);
+                           const int32_t* active, const double* Xoff, double* qr, cudaStream_t s);
+cudaError_t launch_superimpose_stats(const Dims& d, int nb, const double* Xoff, const int32_t* active, double* stat_m,
+                                     double* stat_R, cudaStream_t s);
 cudaError_t launch_enum(const Dims& d, int nb, const double* qr, const double* varn, const int32_t* active,
                         double* stat_m, double* stat_R, int32_t* kstar, double* lse_sym, cudaStream_t s);
 // M-step side (mstep.cu)

@@ -66,7 +66,7 @@ cudaError_t launch_pilot_stats(const Dims& d, int nb, const double* Xp, double* 
 template <int NTX, int NRX>
 __global__ void __launch_bounds__(128) k_heff_qr(Dims d, const cplx* __restrict__ Yd, const cplx* __restrict__ PsiD,
                                                  const cplx* __restrict__ theta, const int32_t* __restrict__ active,
-                                                 double* __restrict__ qr) {
+                                                 const cplx* __restrict__ Xoff, double* __restrict__ qr) {
     constexpr int NR = cmax(NTX, NRX);
     const int b = blockIdx.y;
     if (active != nullptr && active[b] == 0) return;
@@ -95,6 +95,15 @@ __global__ void __launch_bounds__(128) k_heff_qr(Dims d, const cplx* __restrict_
     cplx y[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) y[r] = (r < NRX) ? Yd[((size_t)b * d.T_d + t) * NRX + r] : mk(0.0, 0.0);
+    if (Xoff != nullptr) {   // superimposed pilots: hypotheses are x_k + o_t  <=>  y' = y - Heff o_t
+        const cplx* o = Xoff + ((size_t)b * d.T_d + t) * NTX;
+#pragma unroll
+        for (int j = 0; j < NTX; ++j) {
+            const cplx oj = o[j], noj = mk(-oj.x, -oj.y);
+#pragma unroll
+            for (int r = 0; r < NRX; ++r) cfma(y[r], A[r][j], noj);
+        }
+    }
 
     // Householder, column k; afterwards row k is rotated so that R_kk = ||x|| >= 0 is real
 #pragma unroll
@@ -182,7 +191,8 @@ __device__ __forceinline__ double group8_sum(double v) {
 template <int NTX>
 __global__ void __launch_bounds__(128) k_heff_qr_rows(Dims d, const cplx* __restrict__ Yd,
                                                       const cplx* __restrict__ PsiD, const cplx* __restrict__ theta,
-                                                      const int32_t* __restrict__ active, double* __restrict__ qr) {
+                                                      const int32_t* __restrict__ active,
+                                                      const cplx* __restrict__ Xoff, double* __restrict__ qr) {
     const int b = blockIdx.y;
     if (active != nullptr && active[b] == 0) return;
     const int r = threadIdx.x & 7;
@@ -207,6 +217,14 @@ __global__ void __launch_bounds__(128) k_heff_qr_rows(Dims d, const cplx* __rest
         for (int j = 0; j < NTX; ++j) cfma(A[j], p, __ldg(&row[j * nrx]));
     }
     A[NTX] = Yd[((size_t)b * d.T_d + t) * nrx + rr];
+    if (Xoff != nullptr) {   // superimposed pilots: y' = y - Heff o_t
+        const cplx* o = Xoff + ((size_t)b * d.T_d + t) * NTX;
+#pragma unroll
+        for (int j = 0; j < NTX; ++j) {
+            const cplx oj = o[j];
+            cfma(A[NTX], A[j], mk(-oj.x, -oj.y));
+        }
+    }
     if (!rv) {
 #pragma unroll
         for (int j = 0; j <= NTX; ++j) A[j] = mk(0.0, 0.0);
@@ -723,27 +741,60 @@ __global__ void __launch_bounds__(WARPS * 32, (NTX > 4 ? 2 : 4)) k_enum(Dims d, 
 }
 
 // ---------------------------------------------------------------------------
+// superimposed pilots: statistics of x~ = x + o from those of x
+//   m~_i = m_i + conj(o_i),   R~_ij = R_ij + m_i o_j + conj(o_i) conj(m_j) + conj(o_i) o_j
+// ---------------------------------------------------------------------------
+__global__ void k_superimpose_stats(Dims d, int nb, const cplx* __restrict__ Xoff, const int32_t* __restrict__ active,
+                                    cplx* __restrict__ stat_m, cplx* __restrict__ stat_R) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;   // flat (b, t)
+    if (s >= nb * d.T_d) return;
+    if (active != nullptr && active[s / d.T_d] == 0) return;
+    const int n = d.n_tx;
+    const cplx* o = Xoff + (size_t)s * n;
+    cplx* m = stat_m + (size_t)s * n;
+    cplx* R = stat_R + (size_t)s * n * n;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            cplx v = R[i * n + j];
+            cfma(v, m[i], o[j]);
+            v = cadd(v, cconj(cmul(o[i], m[j])));
+            v = cadd(v, cmulc(o[j], o[i]));   // conj(o_i) o_j
+            R[i * n + j] = v;
+        }
+    for (int i = 0; i < n; ++i) m[i] = cadd(m[i], cconj(o[i]));
+}
+
+cudaError_t launch_superimpose_stats(const Dims& d, int nb, const double* Xoff, const int32_t* active, double* stat_m,
+                                     double* stat_R, cudaStream_t s) {
+    const int total = nb * d.T_d;
+    k_superimpose_stats<<<(total + 127) / 128, 128, 0, s>>>(d, nb, (const cplx*)Xoff, active, (cplx*)stat_m, (cplx*)stat_R);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------
 template <int NTX, int NRX>
 static cudaError_t run_heff(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
-                            const int32_t* active, double* qr, cudaStream_t s) {
+                            const int32_t* active, const double* Xoff, double* qr, cudaStream_t s) {
     dim3 grid((d.T_d + 127) / 128, nb);
-    k_heff_qr<NTX, NRX><<<grid, 128, 0, s>>>(d, (const cplx*)Yd, (const cplx*)PsiD, (const cplx*)theta, active, qr);
+    k_heff_qr<NTX, NRX><<<grid, 128, 0, s>>>(d, (const cplx*)Yd, (const cplx*)PsiD, (const cplx*)theta, active,
+                                             (const cplx*)Xoff, qr);
     count_launch();
     return cudaGetLastError();
 }
 
 template <int NTX>
 static cudaError_t run_heff_ntx(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
-                                const int32_t* active, double* qr, cudaStream_t s) {
+                                const int32_t* active, const double* Xoff, double* qr, cudaStream_t s) {
     switch (d.n_rx) {
-        case 1: return run_heff<NTX, 1>(d, nb, Yd, PsiD, theta, active, qr, s);
-        case 2: return run_heff<NTX, 2>(d, nb, Yd, PsiD, theta, active, qr, s);
-        case 3: return run_heff<NTX, 3>(d, nb, Yd, PsiD, theta, active, qr, s);
-        case 4: return run_heff<NTX, 4>(d, nb, Yd, PsiD, theta, active, qr, s);
-        case 6: return run_heff<NTX, 6>(d, nb, Yd, PsiD, theta, active, qr, s);
-        case 8: return run_heff<NTX, 8>(d, nb, Yd, PsiD, theta, active, qr, s);
+        case 1: return run_heff<NTX, 1>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
+        case 2: return run_heff<NTX, 2>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
+        case 3: return run_heff<NTX, 3>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
+        case 4: return run_heff<NTX, 4>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
+        case 6: return run_heff<NTX, 6>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
+        case 8: return run_heff<NTX, 8>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -776,9 +827,10 @@ static cudaError_t run_enum(const Dims& d, int nb, const double* qr, const doubl
 
 template <int NTX>
 static cudaError_t run_heff_rows(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
-                                 const int32_t* active, double* qr, cudaStream_t s) {
+                                 const int32_t* active, const double* Xoff, double* qr, cudaStream_t s) {
     dim3 grid((d.T_d + 15) / 16, nb);   // 8 lanes per symbol, 16 symbols per CTA
-    k_heff_qr_rows<NTX><<<grid, 128, 0, s>>>(d, (const cplx*)Yd, (const cplx*)PsiD, (const cplx*)theta, active, qr);
+    k_heff_qr_rows<NTX><<<grid, 128, 0, s>>>(d, (const cplx*)Yd, (const cplx*)PsiD, (const cplx*)theta, active,
+                                             (const cplx*)Xoff, qr);
     count_launch();
     return cudaGetLastError();
 }
@@ -807,16 +859,16 @@ static cudaError_t run_enum_ntx(const Dims& d, int nb, const double* qr, const d
 }
 
 cudaError_t launch_heff_qr(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
-                           const int32_t* active, double* qr, cudaStream_t s) {
+                           const int32_t* active, const double* Xoff, double* qr, cudaStream_t s) {
     switch (d.n_tx) {
-        case 1: return run_heff_ntx<1>(d, nb, Yd, PsiD, theta, active, qr, s);
-        case 2: return run_heff_ntx<2>(d, nb, Yd, PsiD, theta, active, qr, s);
-        case 3: return run_heff_ntx<3>(d, nb, Yd, PsiD, theta, active, qr, s);
-        case 4: return run_heff_ntx<4>(d, nb, Yd, PsiD, theta, active, qr, s);
-        case 5: return run_heff_rows<5>(d, nb, Yd, PsiD, theta, active, qr, s);
-        case 6: return run_heff_rows<6>(d, nb, Yd, PsiD, theta, active, qr, s);
-        case 7: return run_heff_rows<7>(d, nb, Yd, PsiD, theta, active, qr, s);
-        case 8: return run_heff_rows<8>(d, nb, Yd, PsiD, theta, active, qr, s);
+        case 1: return run_heff_ntx<1>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
+        case 2: return run_heff_ntx<2>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
+        case 3: return run_heff_ntx<3>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
+        case 4: return run_heff_ntx<4>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
+        case 5: return run_heff_rows<5>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
+        case 6: return run_heff_rows<6>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
+        case 7: return run_heff_rows<7>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
+        case 8: return run_heff_rows<8>(d, nb, Yd, PsiD, theta, active, Xoff, qr, s);
         default: return cudaErrorInvalidValue;
     }
 }

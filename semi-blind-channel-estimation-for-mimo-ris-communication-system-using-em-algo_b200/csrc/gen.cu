@@ -68,18 +68,19 @@ __device__ __forceinline__ cplx cn_sample(const U4& r, double var) {
 // ---------------------------------------------------------------------------
 // channel: Theta[b][n'][j][r]
 // ---------------------------------------------------------------------------
-__global__ void k_gen_channel(Dims d, GenKey key, double varh, cplx* __restrict__ h) {
+__global__ void k_gen_channel(Dims d, GenKey key, double varh, int nodirect, cplx* __restrict__ h) {
     const int b = blockIdx.y;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;   // (n', j, r)
     if (e >= d.L * d.n_rx) return;
     const int r = e % d.n_rx, l = e / d.n_rx, j = l % d.n_tx, np = l / d.n_tx;
     cplx v;
-    if (np == 0) {
+    if (np == 0 && !nodirect) {
         v = cn_sample(draw(key, GS_HBU, b, (uint32_t)(r * d.n_tx + j)), varh);             // H_BU[r][j]
     } else {
-        const int n = np - 1;
+        const int n = nodirect ? np : np - 1;
+        const int nris = nodirect ? d.N1 : d.N;
         const cplx bs = cn_sample(draw(key, GS_HBS, b, (uint32_t)(n * d.n_tx + j)), varh);  // H_BS[n][j]
-        const cplx su = cn_sample(draw(key, GS_HSU, b, (uint32_t)(r * d.N + n)), varh);     // H_SU[r][n]
+        const cplx su = cn_sample(draw(key, GS_HSU, b, (uint32_t)(r * nris + n)), varh);   // H_SU[r][n]
         v = cmul(bs, su);
     }
     h[(size_t)b * d.L * d.n_rx + e] = v;
@@ -114,7 +115,7 @@ __device__ __forceinline__ cplx dft_phase(long long t, long long n, long long de
     return mk(c, s);
 }
 
-__global__ void k_gen_phases(Dims d, GenKey key, int pilot_design, int data_phases, cplx* __restrict__ PsiP,
+__global__ void k_gen_phases(Dims d, GenKey key, int pilot_design, int data_phases, int nodirect, cplx* __restrict__ PsiP,
                              cplx* __restrict__ PsiD) {
     const int b = blockIdx.y;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,7 +125,8 @@ __global__ void k_gen_phases(Dims d, GenKey key, int pilot_design, int data_phas
         if (!PsiP || (d.psi_shared && b > 0)) return;
         const int t = e / d.N1, n1 = e % d.N1;
         cplx v;
-        if (pilot_design == SBCE_PILOTS_PM) v = (n1 < d.N) ? dft_phase(t, n1, d.N) : mk(0.0, 0.0);
+        if (nodirect) v = dft_phase(t, n1, pilot_design == SBCE_PILOTS_PM ? d.N1 : d.T_p);   // all rows are elements
+        else if (pilot_design == SBCE_PILOTS_PM) v = (n1 < d.N) ? dft_phase(t, n1, d.N) : mk(0.0, 0.0);
         else v = (n1 == 0) ? mk(1.0, 0.0) : dft_phase(t, n1 - 1, d.T_p);
         PsiP[(size_t)b * np + e] = v;
     } else {
@@ -133,9 +135,9 @@ __global__ void k_gen_phases(Dims d, GenKey key, int pilot_design, int data_phas
         if (!PsiD || (d.psi_shared && b > 0)) return;
         cplx v;
         if (data_phases == SBCE_PHASES_DFT) v = dft_phase(t, n1, d.T_d);
-        else if (n1 == 0) v = mk(1.0, 0.0);
+        else if (n1 == 0 && !nodirect) v = mk(1.0, 0.0);
         else {
-            const U4 r = draw(key, GS_PHI, b, (uint32_t)(t * d.N + (n1 - 1)));
+            const U4 r = draw(key, GS_PHI, b, nodirect ? (uint32_t)(t * d.N1 + n1) : (uint32_t)(t * d.N + (n1 - 1)));
             double s, c;
             sincospi(2.0 * u53(r.x, r.y), &s, &c);
             v = mk(c, s);
@@ -358,7 +360,7 @@ cudaError_t launch_generate(const Dims& d, int nb, const sbce_gen* g, const sbce
     const GenKey key = make_key(g);
     {
         dim3 grid((d.L * d.n_rx + 255) / 256, nb);
-        k_gen_channel<<<grid, 256, 0, s>>>(d, key, g->varh, (cplx*)h_out);
+        k_gen_channel<<<grid, 256, 0, s>>>(d, key, g->varh, g->no_direct_link ? 1 : 0, (cplx*)h_out);
         count_launch();
     }
     {
@@ -368,7 +370,8 @@ cudaError_t launch_generate(const Dims& d, int nb, const sbce_gen* g, const sbce
     }
     {
         dim3 grid(((d.T_p + d.T_d) * d.N1 + 255) / 256, d.psi_shared ? 1 : nb);
-        k_gen_phases<<<grid, 256, 0, s>>>(d, key, g->pilot_design, g->data_phases, (cplx*)PsiP_out, (cplx*)PsiD_out);
+        k_gen_phases<<<grid, 256, 0, s>>>(d, key, g->pilot_design, g->data_phases, g->no_direct_link ? 1 : 0, (cplx*)PsiP_out,
+                                         (cplx*)PsiD_out);
         count_launch();
     }
     if (d.T_p > 0) {

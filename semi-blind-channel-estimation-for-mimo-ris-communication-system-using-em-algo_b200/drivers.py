@@ -44,6 +44,7 @@ class SweepConfig:
     legacy_rng: bool = True
     seed: int = 0
     max_batch: int = 4096         # trials per library call
+    direct_link: bool = True      # False: no BS-user link, L = N n_tx ("direct vs non direct - T_pv s nmse.py"); on_device only
     on_device: bool = False       # generate inputs + LS start on the GPU (Philox; sbce_generate_batch / sbce_ls_start):
                                   # nothing but the per-point accumulators crosses PCIe
 
@@ -84,8 +85,9 @@ def run_point_device(cfg: SweepConfig, point_index: int, device=0, per_trial=Non
 
     rank, ws = dist.world()
     lo, hi = dist.shard_trials(cfg.monte_iter, rank, ws)
-    prob = engine.Problem(N=cfg.N, n_tx=cfg.n_tx, n_rx=cfg.n_rx, M=cfg.M, T_p=cfg.T_p, T_d=cfg.T_d, itera=cfg.itera,
-                          mode=cfg.mode, genie_stop=cfg.genie_stop, quirks=cfg.quirks,
+    # without the direct link every phase row is a RIS element: N rows instead of N + 1
+    prob = engine.Problem(N=cfg.N if cfg.direct_link else cfg.N - 1, n_tx=cfg.n_tx, n_rx=cfg.n_rx, M=cfg.M, T_p=cfg.T_p,
+                          T_d=cfg.T_d, itera=cfg.itera, mode=cfg.mode, genie_stop=cfg.genie_stop, quirks=cfg.quirks,
                           zero_start=(cfg.start == "zero"), partition_r=cfg.partition_r)
     acc = PointResult()
     if hi <= lo:
@@ -104,7 +106,7 @@ def run_point_device(cfg: SweepConfig, point_index: int, device=0, per_trial=Non
         for b0 in range(lo, hi, cfg.max_batch):
             nb = min(cfg.max_batch, hi - b0)
             tb = ses.generate(nb, cfg.varn, seed=cfg.seed * 1000003 + point_index, trial0=b0, pilot_design=pilot,
-                              data_phases=phases)
+                              data_phases=phases, direct_link=cfg.direct_link)
             theta0, st0 = (None, None) if prob.zero_start else ses.ls_start(tb["Yp"], tb["PsiP"], tb["Xp"])
             res = ses.run(tb["Yd"], tb["Yp"], tb["PsiD"], tb["PsiP"], tb["Xp"], tb["varn"], theta0=theta0,
                           h_true=tb["h"])

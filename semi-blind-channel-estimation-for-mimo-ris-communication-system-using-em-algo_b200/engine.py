@@ -17,7 +17,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import (FLAG_FULL_SCAN, FLAG_GENIE_STOP, FLAG_PSI_SHARED, FLAG_QUIRKS, FLAG_ZERO_START, MODE_HARD,
+from ._lib import (FLAG_FULL_SCAN, FLAG_GENIE_STOP, FLAG_PSI_SHARED, FLAG_QUIRKS, FLAG_SUPERIMPOSED, FLAG_ZERO_START, MODE_HARD,
                    MODE_MMSE, MODE_PM, MODE_PM_BETA, MODE_SOFT, MODE_ZF)
 
 MODES = {"soft": MODE_SOFT, "hard": MODE_HARD, "pm": MODE_PM, "pm_beta": MODE_PM_BETA, "zf": MODE_ZF,
@@ -42,6 +42,7 @@ class Problem:
     psi_shared: bool = False
     partition_r: float = 0.0
     full_scan: bool = False   # E-step visits every tree node instead of skipping provably weightless subtrees
+    superimposed: bool = False  # parallel protocol (Parallel/ParallelProtocol_Tp.py): Xp holds per-symbol offsets, T_p = 0
 
     @property
     def L(self):
@@ -59,6 +60,7 @@ class Problem:
         flags |= FLAG_PSI_SHARED if self.psi_shared else 0
         flags |= FLAG_ZERO_START if self.zero_start else 0
         flags |= FLAG_FULL_SCAN if self.full_scan else 0
+        flags |= FLAG_SUPERIMPOSED if self.superimposed else 0
         c = _lib.Cfg()
         c.N, c.n_tx, c.n_rx, c.M = self.N, self.n_tx, self.n_rx, self.M
         c.T_p, c.T_d, c.itera, c.batch = self.T_p, self.T_d, self.itera, batch
@@ -68,7 +70,8 @@ class Problem:
     def shapes(self, B):
         pb = () if self.psi_shared else (B,)
         return dict(Yd=(B, self.T_d, self.n_rx), Yp=(B, self.T_p, self.n_rx), PsiD=pb + (self.T_d, self.N + 1),
-                    PsiP=pb + (self.T_p, self.N + 1), Xp=(B, self.T_p, self.n_tx), theta0=(B, self.L, self.n_rx),
+                    PsiP=pb + (self.T_p, self.N + 1), Xp=(B, self.T_d if self.superimposed else self.T_p, self.n_tx),
+                    theta0=(B, self.L, self.n_rx),
                     h_true=(B, self.L, self.n_rx), Xd_true=(B, self.T_d, self.n_tx))
 
 
@@ -314,7 +317,7 @@ class DeviceSession:
 
 
     # ---- on-device generation + LS start (include/sbce.h: sbce_generate_batch, sbce_ls_start) ----
-    def generate(self, B, varn, seed, trial0=0, pilot_design="pm", data_phases="random", varh=1.0):
+    def generate(self, B, varn, seed, trial0=0, pilot_design="pm", data_phases="random", varh=1.0, direct_link=True):
         """Philox-generated trials written straight into device tensors (same names as
         signal_model.TrialBatch: h, Xd, Xp, PsiP, PsiD, Yp, Yd, varn).  Trial b of the batch is global
         trial trial0 + b of the sweep keyed by `seed`, independent of batch size and sharding."""
@@ -335,6 +338,7 @@ class DeviceSession:
         g = _lib.Gen()
         g.seed, g.trial0 = int(seed) & (2 ** 64 - 1), int(trial0)
         g.pilot_design, g.data_phases, g.varh = _lib.PILOTS[pilot_design], _lib.PHASES_KIND[data_phases], float(varh)
+        g.no_direct_link = 0 if direct_link else 1   # all Problem.N + 1 phase rows are RIS elements
         cfg = p.cfg(B)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(self.lib.sbce_generate_batch(C.byref(cfg), C.byref(g), C.byref(io), stream))

@@ -108,6 +108,30 @@ def em_ml(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, all_possibleSymbols, M, varn, it
     return res.theta.reshape(-1, 1)
 
 
+def em_parallel(Y, T, Z, X_d, X_p, T_p, T_d, n_tx, PsiTilde_t, all_possibleSymbols, M, varn, itera, N, *, hard=False,
+                device=0):
+    """Parallel protocol with superimposed pilots: the reference's `em` of Parallel/ParallelProtocol_Tp.py:64
+    (same positional signature).  Hypotheses of symbol t are x_k + x_p[t] (zero beyond T_p), no separate pilot
+    term, zero start.  Z and X_d are accepted for signature compatibility and not used (as in the reference)."""
+    cons = constellation_from_table(all_possibleSymbols, M)
+    if M not in SUPPORTED_M or not np.array_equal(np.asarray(cons, dtype=np.complex128), constellation(M)):
+        raise ValueError("only the reference's un-normalised square QAM constellation is supported")
+    Yd = _stack_cols(Y)
+    n_rx = Yd.shape[1]
+    Psi = np.asarray(PsiTilde_t, dtype=np.complex128).T.copy()
+    if Yd.shape[0] != T or Psi.shape != (T, N + 1):
+        raise ValueError("T does not match Y / PsiTilde_t")
+    Xoff = np.zeros((T, n_tx), dtype=np.complex128)
+    if T_p:
+        Xoff[:T_p] = _stack_cols(X_p)
+    prob = engine.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=0, T_d=T, itera=int(itera), mode="hard" if hard else "soft",
+                          zero_start=True, superimposed=True)
+    empty = np.zeros((1, 0, n_rx), np.complex128)
+    res = engine.run_host(prob, Yd[None], empty, Psi[None], np.zeros((1, 0, N + 1), np.complex128), Xoff[None],
+                          float(varn), device=device)
+    return res.theta.reshape(-1, 1)
+
+
 def _true_data_from_Zd(Z_d, PsiTilde_td, n_rx, n_tx):
     Psi = np.asarray(PsiTilde_td)
     T_d = len(Z_d)

@@ -89,6 +89,32 @@ def test_device_generator_matches_restatement(S, case):
 
 
 @gpu
+@pytest.mark.parametrize("case", [(8, 2, 2, 4, 12, 30, 0.1, "pm", "random"), (5, 3, 4, 16, 9, 14, 0.4, "top", "dft")])
+def test_device_generator_no_direct_link(S, case):
+    """All N + 1 phase rows are RIS elements (no ones row, no H_BU): "direct vs non direct - T_pv s nmse.py"."""
+    from oracle import em_numpy as orc
+    from oracle.philox import generate_trial
+
+    N, n_tx, n_rx, M, T_p, T_d, varn, pilot, phases = case
+    B, seed = 2, 5
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=3, zero_start=True)
+    ses = S.DeviceSession(prob, B)
+    dv = ses.generate(B, varn, seed, pilot_design=pilot, data_phases=phases, direct_link=False)
+    tb = {k: v.cpu().numpy() for k, v in dv.items()}
+    for b in range(B):
+        g = generate_trial(N, n_tx, n_rx, M, T_p, T_d, varn, seed, b, pilot, phases, direct_link=False)
+        assert np.array_equal(tb["Xd"][b], g["Xd"]) and np.array_equal(tb["Xp"][b], g["Xp"])
+        for k in ("h", "PsiP", "PsiD", "Yp", "Yd"):
+            assert np.abs(tb[k][b] - g[k]).max() < 1e-12 * max(1.0, np.abs(g[k]).max()), k
+        assert np.allclose(np.abs(tb["PsiD"][b]), 1.0) and np.allclose(np.abs(tb["PsiP"][b]), 1.0)
+    res = ses.run(dv["Yd"], dv["Yp"], dv["PsiD"], dv["PsiP"], dv["Xp"], dv["varn"], h_true=dv["h"])
+    theta = res.theta.cpu().numpy()
+    for b in range(B):
+        ref = orc.em(tb["Yd"][b], tb["Yp"][b], tb["PsiD"][b], tb["PsiP"][b], tb["Xp"][b], M, varn, 3, theta0=None)
+        assert relerr(theta[b], ref) < 1e-9
+
+
+@gpu
 def test_generation_is_sharding_invariant(S):
     N, n_tx, n_rx, M, T_p, T_d = 8, 2, 2, 16, 12, 20
     prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=1)

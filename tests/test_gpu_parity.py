@@ -216,6 +216,67 @@ def test_em_soft_golden(S, orc, name):
     assert abs(S.nmse(theta, g["h"]) - g["nmse_ref"]) <= 1e-8 * max(1.0, g["nmse_ref"])
 
 
+@pytest.mark.parametrize("name", golden_names("nodirect"))
+def test_em_no_direct_link_golden(S, orc, name):
+    """No-direct-link layout of `direct vs non direct - T_pv s nmse.py` through the reference-signature
+    entry point: N phase rows, L = N n_tx; and the same data with the direct link (`em_direct_in`)."""
+    meta, g = load_golden(name)
+    n_tx, n_rx, M = int(meta["n_tx"]), int(meta["n_rx"]), int(meta["M"])
+    T_d, T_p, varn, itera = int(meta["T_d"]), int(meta["T_p"]), float(meta["varn"]), int(meta["itera"])
+    table = orc.hypothesis_table(orc.qam_constellation(M), n_tx)
+    Y_d, Y_p, Z_p, PsiTilde_td = _ref_objects(g, n_rx)
+    theta = S.em(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, table, M, varn, itera, None)
+    assert theta.shape == (int(meta["N"]) * n_tx * n_rx, 1)
+    assert relerr(theta.reshape(g["theta_ref"].shape), g["theta_ref"]) < RTOL
+    g1 = {k[4:]: v for k, v in g.items() if k.startswith("din_")}
+    Y_d, Y_p, Z_p, PsiTilde_td = _ref_objects(g1, n_rx)
+    theta = S.em(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, table, M, varn, itera, None)
+    assert relerr(theta.reshape(g1["theta_ref"].shape), g1["theta_ref"]) < RTOL
+
+
+@pytest.mark.parametrize("name", golden_names("parallel"))
+def test_em_parallel_golden(S, orc, name):
+    """Superimposed pilots (`Parallel/ParallelProtocol_Tp.py:64`) through the reference-signature entry point."""
+    meta, g = load_golden(name)
+    n_tx, n_rx, M, N = int(meta["n_tx"]), int(meta["n_rx"]), int(meta["M"]), int(meta["N"])
+    T, T_p, T_d = int(meta["T"]), int(meta["T_p"]), int(meta["T_d"])
+    table = orc.hypothesis_table(orc.qam_constellation(M), n_tx)
+    Y = [g["Y"][t].reshape(-1, 1) for t in range(T)]
+    X_p = [g["Xp"][t].reshape(-1, 1) for t in range(T_p)]
+    X_d = [g["Xd"][t].reshape(-1, 1) for t in range(T_d)]
+    theta = S.em_parallel(Y, T, None, X_d, X_p, T_p, T_d, n_tx, g["Psi"].T.copy(), table, M, float(meta["varn"]),
+                          int(meta["itera"]), N)
+    assert relerr(theta.reshape(g["theta_ref"].shape), g["theta_ref"]) < RTOL
+
+
+@pytest.mark.parametrize("case", [(8, 2, 2, 16, 12, 40, 4, 0.3, False), (6, 3, 4, 4, 50, 30, 3, 0.5, True),
+                                  (10, 4, 4, 4, 20, 60, 3, 0.2, False), (5, 6, 8, 4, 10, 48, 2, 0.4, False)])
+def test_em_superimposed_batch_matches_oracle(S, orc, case):
+    """Superimposed pilots, batched, incl. the wide-array E-step: decisions bit-exact, theta 1e-9."""
+    N, n_tx, n_rx, M, T_p, T_d, itera, varn, hard = case
+    B, T = 3, max(T_p, T_d)
+    rng = np.random.default_rng(12)
+    cons = orc.qam_constellation(M)
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, 2, T, varn, B, seed=8, legacy=False, variant="top_td")
+    Xoff = np.zeros((B, T, n_tx), np.complex128)
+    Xoff[:, :T_p] = cons[rng.integers(0, M, (B, T_p, n_tx))]
+    Xd = np.zeros((B, T, n_tx), np.complex128)
+    Xd[:, :T_d] = cons[rng.integers(0, M, (B, T_d, n_tx))]
+    W = (tb.PsiD[:, :, :, None] * (Xd + Xoff)[:, :, None, :]).reshape(B, T, -1)
+    Y = W @ tb.h + np.sqrt(varn / 2) * (rng.standard_normal((B, T, n_rx)) + 1j * rng.standard_normal((B, T, n_rx)))
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=0, T_d=T, itera=itera, mode="hard" if hard else "soft",
+                     zero_start=True, superimposed=True)
+    res = S.run_host(prob, Y, np.zeros((B, 0, n_rx), np.complex128), tb.PsiD, np.zeros((B, 0, N + 1), np.complex128),
+                     Xoff, tb.varn, h_true=tb.h)
+    assert (res.status == 0).all()
+    for b in range(B):
+        ref, tr = orc.em_superimposed(Y[b], tb.PsiD[b], Xoff[b], M, varn, itera, hard=hard, return_trace=True)
+        assert relerr(res.theta[b], ref) < RTOL
+        assert np.array_equal(res.kstar[b], tr["kstar"])
+        if not hard:   # (hard mode reports -min d2 / varn^2, not the log-sum)
+            np.testing.assert_allclose(res.lse[b], np.array(tr["lse"]), rtol=1e-9)
+
+
 @pytest.mark.parametrize("name", golden_names("hard"))
 def test_em_hard_golden(S, orc, name):
     meta, g = load_golden(name)

@@ -55,6 +55,29 @@ def test_soft_em_matches_reference(name):
     assert abs(orc.nmse(th, g["h"]) - g["nmse_ref"]) <= 1e-9 * max(1.0, g["nmse_ref"])
 
 
+@pytest.mark.parametrize("name", golden_names("nodirect"))
+def test_no_direct_link_layout_matches_reference(name):
+    """`direct vs non direct - T_pv s nmse.py`: the estimator is agnostic to what the phase rows mean, so the
+    no-direct-link model (N phase rows, L = N n_tx) is the same code with one row less."""
+    meta, g = load_golden(name)
+    M, varn, itera = int(meta["M"]), float(meta["varn"]), int(meta["itera"])
+    assert g["PsiD"].shape[1] == int(meta["N"]) and g["din_PsiD"].shape[1] == int(meta["N"]) + 1
+    th = orc.em(g["Yd"], g["Yp"], g["PsiD"], g["PsiP"], g["Xp"], M, varn, itera, theta0=None)
+    assert relerr(th, g["theta_ref"]) < RTOL_THETA
+    th1 = orc.em(g["din_Yd"], g["din_Yp"], g["din_PsiD"], g["din_PsiP"], g["din_Xp"], M, varn, itera, theta0=None)
+    assert relerr(th1, g["din_theta_ref"]) < RTOL_THETA
+    assert abs(orc.nmse(th, g["h"]) - g["nmse_ref"]) <= 1e-9 * max(1.0, g["nmse_ref"])
+
+
+@pytest.mark.parametrize("name", golden_names("parallel"))
+def test_superimposed_pilots_match_reference(name):
+    """`Parallel/ParallelProtocol_Tp.py`: hypotheses x_k + x_p[t], no pilot term, zero start."""
+    meta, g = load_golden(name)
+    th = orc.em_superimposed(g["Y"], g["Psi"], g["Xoff"], int(meta["M"]), float(meta["varn"]), int(meta["itera"]))
+    assert relerr(th, g["theta_ref"]) < RTOL_THETA
+    assert abs(orc.nmse(th, g["h"]) - g["nmse_ref"]) <= 1e-9 * max(1.0, g["nmse_ref"])
+
+
 def test_known_answers_of_baseline_md():
     """BASELINE.md section 3.2 row 3 (seed 1234)."""
     meta, g = load_golden("soft_rev4_s1234")
