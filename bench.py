@@ -8,7 +8,8 @@ Proposed_method_NMSEvsTd.py scaled to N=64 RIS elements, 4x4 MIMO, 16-QAM (K = 6
 hypotheses per data symbol), T_p=320, T_d=256, 10 EM iterations, soft-decision EM from the LS start,
 varn=0.1 -- an operating point where the LS start is identifiable (T_p >= L=260) and EM improves the
 NMSE ~25x (1.3e-2 -> 5.6e-4, measured); at the reference's T_p=16 the M-step is singular at this L.  A "step" is one batched call of the hot path over
-`B` independent Monte-Carlo trials per GPU; trials are sharded across ranks (disjoint seeds, no
+`B` = 1184 independent Monte-Carlo trials per GPU (eight per SM; the host-buffer entry point pipelines the batch
+in two halves so that the upload of the second overlaps the kernels of the first); trials are sharded across ranks (disjoint seeds, no
 data-path collective) -> weak scaling.
 
 Prints ONE JSON line (rank 0).  `value` = trials/s with inputs resident in HBM (CUDA-event
@@ -202,11 +203,15 @@ def run_ours(args):
     w = dict(WORKLOAD)
     B = args.trials_per_step
     prob = engine.Problem(N=w["N"], n_tx=w["n_tx"], n_rx=w["n_rx"], M=w["M"], T_p=w["T_p"], T_d=w["T_d"],
-                          itera=w["itera"], mode=w["mode"])
+                          itera=w["itera"], mode=w["mode"], psip_shared=True)
     # synthetic inputs, generated once by numpy on the host (disjoint seed per rank)
     tb = signal_model.generate_batch(w["N"], w["n_tx"], w["n_rx"], w["M"], w["T_p"], w["T_d"], w["varn"], B,
                                      seed=20260 + 7919 * rank, legacy=False, variant=PILOT_DESIGN)
-    host_in = dict(Yd=tb.Yd, Yp=tb.Yp, PsiD=tb.PsiD, PsiP=tb.PsiP, Xp=tb.Xp, theta0=tb.theta0, h_true=tb.h)
+    # the pilot design is deterministic (identical for every trial): passed once (SBCE_FLAG_PSIP_SHARED);
+    # data phases, symbols, channels and noise are per trial
+    assert (tb.PsiP == tb.PsiP[0]).all()
+    host_in = dict(Yd=tb.Yd, Yp=tb.Yp, PsiD=tb.PsiD, PsiP=np.ascontiguousarray(tb.PsiP[0]), Xp=tb.Xp, theta0=tb.theta0,
+                   h_true=tb.h)
     t_dev = {k: torch.from_numpy(v).to(dev) for k, v in host_in.items()}
     varn_dev = torch.from_numpy(tb.varn).to(dev)
     input_bytes = sum(v.nbytes for v in host_in.values()) + tb.varn.nbytes
@@ -303,6 +308,21 @@ def run_ours(args):
     e2e_steps = max(1, min(args.steps, 5))
     e2e_step()
     barrier()
+    # plain pinned-host -> device copy rate of this box (explains how far e2e can sit below `value`)
+    big = max(pin.values(), key=lambda a: a.nbytes)
+    tsrc = torch.from_numpy(big)
+    tdst = torch.empty(tsrc.shape, dtype=tsrc.dtype, device=dev)
+    tdst.copy_(tsrc, non_blocking=True)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        tdst.copy_(tsrc, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * big.nbytes / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del tdst
+    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()          # synchronous: returns after the D2H copies completed
@@ -351,7 +371,8 @@ def run_ours(args):
     top = max((n for n in kernels if n in fm), key=lambda n: kernels[n]["ms_total"])
     roofline = dict(bound="tensor", pipe="FP64 tensor path (mma.sync DMMA; tcgen05 has no FP64 kind)", kernel=top, achieved=kernels[top]["tflops"], peak=fp64_peak, unit="TFLOP/s",
                     frac=kernels[top]["frac_fp64_peak"],
-                    traffic=(ncu_traffic.get(top) if (B == 592 and w == WORKLOAD) else None),
+                    # measured at 592 trials per launch; every kernel's traffic is linear in the trial count
+                    traffic=(ncu_traffic.get(top) * (B / 592.0) if (top in ncu_traffic and w == WORKLOAD) else None),
                     traffic_unit="bytes per launch (ncu dram read+write, profiles/r01k_top_kernels_full.csv)",
                     share_of_step=kernels[top]["share"],
                     peak_source="live DFMA micro-benchmark in libsbce (2 flop/FMA); MEASURED_PEAKS.json has no FP64 entry",
@@ -384,12 +405,13 @@ def run_ours(args):
                 ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64", data="synthetic",
                 config=dict(workload=workload_name(w), trials_per_step_per_gpu=B, pilot_design=PILOT_DESIGN,
+                            layout="deterministic pilot phases passed once per batch; data phases, symbols, channels per trial",
                             enumeration="exact posterior over all M^n_tx hypotheses; subtrees that provably carry no "
                                         "weight (partial distance > incumbent + 64 varn^2) are skipped, outputs "
                                         "bit-identical to the full scan (see full_scan)",
                             l2="inputs (%.0f MB per GPU) larger than the 126 MB L2" % (input_bytes / 1e6), **w),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(input_bytes), d2h_bytes_per_step=int(d2h_bytes),
-                         steps=e2e_steps),
+                         steps=e2e_steps, h2d_gbs_measured=h2d_gbs),
                 gpu_launches=int(launches), clocks=clocks, roofline=roofline, kernels=kernels, cpu_baseline=cpu,
                 full_scan=full,
                 check=dict(nmse_mean=nmse_mean, nmse_ls_start=nmse_init, flagged_trials=int((st != 0).sum())))
@@ -406,7 +428,7 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--trials-per-step", type=int, default=592)
+    ap.add_argument("--trials-per-step", type=int, default=1184)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-scan", action="store_true")
     args = ap.parse_args()

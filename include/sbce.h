@@ -69,6 +69,11 @@ extern "C" {
                                    o_t (pilot symbol, zero beyond the pilot length), there is no separate pilot block:
                                    T_p must be 0 and io->Xp holds the offsets [B][T_d][n_tx]; soft / hard modes only */
 
+#define SBCE_FLAG_PSIP_SHARED 64u  /* only the PILOT phases PsiP are shared by all trials ([T_p][N+1]); data phases stay per
+                                   trial.  The reference's pilot designs are deterministic DFT patterns (PM.py:120-124,
+                                   Proposed_method_NMSEvsTp.py:77) while its data phases are redrawn per trial (PM.py:125-129):
+                                   passing the pilot design once halves the input volume of a sweep point */
+
 /* per-trial status bits */
 #define SBCE_ST_NOT_PD 1    /* non-positive pivot in the Cholesky of the normal matrix (singular M-step) */
 #define SBCE_ST_NONFINITE 2 /* a non-finite value appeared in theta                                      */
@@ -99,7 +104,7 @@ typedef struct sbce_io {
     const double* Yd;      /* [B][T_d][n_rx]                                                   */
     const double* Yp;      /* [B][T_p][n_rx]                                                   */
     const double* PsiD;    /* [B][T_d][N+1]  (or [T_d][N+1] with SBCE_FLAG_PSI_SHARED)          */
-    const double* PsiP;    /* [B][T_p][N+1]  (or [T_p][N+1])                                   */
+    const double* PsiP;    /* [B][T_p][N+1]  (or [T_p][N+1] with SBCE_FLAG_PSI_SHARED / _PSIP_SHARED) */
     const double* Xp;      /* [B][T_p][n_tx] pilot symbols  ([B][T_d][n_tx] offsets with SBCE_FLAG_SUPERIMPOSED) */
     const double* theta0;  /* [B][L][n_rx]   start point; nullable with SBCE_FLAG_ZERO_START   */
     const double* varn;    /* [B] float64 -- the E-step divides by varn^2 (reference quirk Q1) */

@@ -65,6 +65,7 @@ static int make_dims(const sbce_cfg* c, Dims* d, bool with_estep = true) {
     d->Ltot = d->Lp + d->RP;
     d->mode = c->mode; d->flags = c->flags; d->p1 = c->partition_p1;
     d->psi_shared = (c->flags & SBCE_FLAG_PSI_SHARED) ? 1 : 0;
+    d->psiP_shared = (c->flags & (SBCE_FLAG_PSI_SHARED | SBCE_FLAG_PSIP_SHARED)) ? 1 : 0;
     d->rec = qr_record_doubles(c->n_tx);
     if (c->mode == SBCE_MODE_PM || c->mode == SBCE_MODE_PM_BETA) {
         if (c->partition_p1 < 1 || c->partition_p1 > c->n_tx) return SBCE_E_SHAPE;
@@ -134,6 +135,9 @@ static int estep_dispatch(const Dims& d, int nb, const double* Yd, const double*
     return 0;
 }
 
+// dims as seen by kernels that are handed the PILOT phase matrix
+static inline Dims pilot_dims(const Dims& d) { Dims dp = d; dp.psi_shared = d.psiP_shared; return dp; }
+
 static int em_chunk(const Dims& d, int nb, const sbce_io& io, Workspace& ws, cudaStream_t s) {
     {
         PhaseScope ps(SBCE_PHASE_SETUP, s);
@@ -141,7 +145,7 @@ static int em_chunk(const Dims& d, int nb, const sbce_io& io, Workspace& ws, cud
         // pilot part of the normal equations, once (the reference recomputes it every iteration:
         // Proposed_method_NMSEvsTp.py:63-65)
         CK(launch_pilot_stats(d, nb, io.Xp, ws.pil_m, ws.pil_R, s));
-        CK(launch_normal_equations(d, nb, io.PsiP, d.T_p, io.Yp, ws.pil_m, ws.pil_R, nullptr, ws.Gp, nullptr, s));
+        CK(launch_normal_equations(pilot_dims(d), nb, io.PsiP, d.T_p, io.Yp, ws.pil_m, ws.pil_R, nullptr, ws.Gp, nullptr, s));
     }
     for (int l = 0; l < d.itera; ++l) {
         int rc = estep_dispatch(d, nb, io.Yd, io.PsiD, io.theta, io.varn, ws.active, ws, ws.stat_m, ws.stat_R,
@@ -176,10 +180,8 @@ static sbce_io offset_io(const Dims& d, const sbce_io& io, size_t b0) {
     auto advw = [](double* p, size_t n) { return p ? p + n : p; };
     o.Yd = adv(io.Yd, b0 * d.T_d * d.n_rx * 2);
     o.Yp = adv(io.Yp, b0 * d.T_p * d.n_rx * 2);
-    if (!d.psi_shared) {
-        o.PsiD = adv(io.PsiD, b0 * d.T_d * d.N1 * 2);
-        o.PsiP = adv(io.PsiP, b0 * d.T_p * d.N1 * 2);
-    }
+    if (!d.psi_shared) o.PsiD = adv(io.PsiD, b0 * d.T_d * d.N1 * 2);
+    if (!d.psiP_shared) o.PsiP = adv(io.PsiP, b0 * d.T_p * d.N1 * 2);
     o.Xp = adv(io.Xp, b0 * ((d.flags & SBCE_FLAG_SUPERIMPOSED) ? d.T_d : d.T_p) * d.n_tx * 2);
     o.theta0 = adv(io.theta0, b0 * Ln);
     o.varn = adv(io.varn, b0);
@@ -318,7 +320,7 @@ int sbce_mstep(const sbce_cfg* cfg, const sbce_io* io, const double* stat_m, con
         const size_t sb = (size_t)b0 * d.T_d;
         CK(cudaMemsetAsync(ws.stat, 0, (size_t)nb * 4, s));
         CK(launch_pilot_stats(d, nb, o.Xp, ws.pil_m, ws.pil_R, s));
-        CK(launch_normal_equations(d, nb, o.PsiP, d.T_p, o.Yp, ws.pil_m, ws.pil_R, nullptr, ws.Gp, nullptr, s));
+        CK(launch_normal_equations(pilot_dims(d), nb, o.PsiP, d.T_p, o.Yp, ws.pil_m, ws.pil_R, nullptr, ws.Gp, nullptr, s));
         CK(launch_normal_equations(d, nb, o.PsiD, d.T_d, o.Yd, stat_m + sb * d.n_tx * 2,
                                    stat_R + sb * d.n_tx * d.n_tx * 2, ws.Gp, ws.G, nullptr, s));
         CK(launch_chol_solve(d, nb, ws.G, theta_out + (size_t)b0 * d.L * d.n_rx * 2, nullptr, ws.stat, ws.thbuf, s));
@@ -363,7 +365,7 @@ int sbce_ls_start(const sbce_cfg* cfg, const sbce_io* io, double* theta0, int32_
         Workspace ws;
         carve_workspace(d, nb, workspace, &ws);
         sbce_io o = offset_io(d, *io, (size_t)b0);
-        CK(launch_ls_start(d, nb, o, theta0 + (size_t)b0 * d.L * d.n_rx * 2, status ? status + b0 : nullptr, ws,
+        CK(launch_ls_start(pilot_dims(d), nb, o, theta0 + (size_t)b0 * d.L * d.n_rx * 2, status ? status + b0 : nullptr, ws,
                            (cudaStream_t)stream));
     }
     return 0;
@@ -465,7 +467,7 @@ int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device) {
     CK(cudaSetDevice(device));
     const size_t B = (size_t)cfg->batch;
     const size_t Ln = (size_t)d.L * d.n_rx * 16;
-    const size_t psiB = d.psi_shared ? 1 : B;
+    const size_t psiB = d.psi_shared ? 1 : B, psiPB = d.psiP_shared ? 1 : B;
     // device mirror of the io block
     struct Seg { const void* h; size_t bytes; size_t off; bool in; void* hout; };
     size_t off = 0;
@@ -477,7 +479,7 @@ int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device) {
     Seg sYd = seg(io->Yd, B * d.T_d * d.n_rx * 16, true, nullptr);
     Seg sYp = seg(io->Yp, B * d.T_p * d.n_rx * 16, true, nullptr);
     Seg sPd = seg(io->PsiD, psiB * d.T_d * d.N1 * 16, true, nullptr);
-    Seg sPp = seg(io->PsiP, psiB * d.T_p * d.N1 * 16, true, nullptr);
+    Seg sPp = seg(io->PsiP, psiPB * d.T_p * d.N1 * 16, true, nullptr);
     const size_t xpT = (d.flags & SBCE_FLAG_SUPERIMPOSED) ? d.T_d : d.T_p;   // offsets ride in Xp
     Seg sXp = seg(io->Xp, B * xpT * d.n_tx * 16, true, nullptr);
     Seg sT0 = seg(io->theta0, B * Ln, true, nullptr);
@@ -520,7 +522,7 @@ int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device) {
     const int half = (cfg->batch + nhalf - 1) / nhalf;
     struct Part { Seg* q; size_t per_trial; };
     Part ins[] = {{&sYd, (size_t)d.T_d * d.n_rx * 16}, {&sYp, (size_t)d.T_p * d.n_rx * 16},
-                  {&sPd, d.psi_shared ? 0 : (size_t)d.T_d * d.N1 * 16}, {&sPp, d.psi_shared ? 0 : (size_t)d.T_p * d.N1 * 16},
+                  {&sPd, d.psi_shared ? 0 : (size_t)d.T_d * d.N1 * 16}, {&sPp, d.psiP_shared ? 0 : (size_t)d.T_p * d.N1 * 16},
                   {&sXp, xpT * d.n_tx * 16}, {&sT0, Ln}, {&sVn, 8}, {&sHt, Ln},
                   {&sXd, (size_t)d.T_d * d.n_tx * 16}};
     Part outs[] = {{&oTh, Ln}, {&oKs, (size_t)d.T_d * 4}, {&oLl, (size_t)d.itera * 8}, {&oLs, (size_t)d.itera * 8},

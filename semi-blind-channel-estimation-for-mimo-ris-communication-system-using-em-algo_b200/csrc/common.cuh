@@ -64,7 +64,8 @@ struct Dims {
     int mode;
     unsigned flags;
     int p1;     // PM: streams enumerated exhaustively
-    int psi_shared;
+    int psi_shared;   // the phase matrix a kernel is handed has no batch dimension (data phases in the EM loop)
+    int psiP_shared;  // ... the pilot phases (launchers of pilot-side kernels copy this into psi_shared)
     int rec;    // doubles per per-symbol QR record
 };
 

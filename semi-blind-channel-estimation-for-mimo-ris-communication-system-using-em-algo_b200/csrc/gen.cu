@@ -122,7 +122,7 @@ __global__ void k_gen_phases(Dims d, GenKey key, int pilot_design, int data_phas
     const int np = d.T_p * d.N1, nd = d.T_d * d.N1;
     if (e >= np + nd) return;
     if (e < np) {
-        if (!PsiP || (d.psi_shared && b > 0)) return;
+        if (!PsiP || (d.psiP_shared && b > 0)) return;
         const int t = e / d.N1, n1 = e % d.N1;
         cplx v;
         if (nodirect) v = dft_phase(t, n1, pilot_design == SBCE_PILOTS_PM ? d.N1 : d.T_p);   // all rows are elements
@@ -369,14 +369,16 @@ cudaError_t launch_generate(const Dims& d, int nb, const sbce_gen* g, const sbce
         count_launch();
     }
     {
-        dim3 grid(((d.T_p + d.T_d) * d.N1 + 255) / 256, d.psi_shared ? 1 : nb);
+        dim3 grid(((d.T_p + d.T_d) * d.N1 + 255) / 256, (d.psi_shared && d.psiP_shared) ? 1 : nb);
         k_gen_phases<<<grid, 256, 0, s>>>(d, key, g->pilot_design, g->data_phases, g->no_direct_link ? 1 : 0, (cplx*)PsiP_out,
                                          (cplx*)PsiD_out);
         count_launch();
     }
     if (d.T_p > 0) {
         dim3 grid((d.T_p + 3) / 4, nb);
-        k_gen_received<<<grid, 128, 0, s>>>(d, key, d.T_p, GS_NP, (const cplx*)PsiP_out, (const cplx*)Xp_out,
+        Dims dp = d;
+        dp.psi_shared = d.psiP_shared;
+        k_gen_received<<<grid, 128, 0, s>>>(dp, key, d.T_p, GS_NP, (const cplx*)PsiP_out, (const cplx*)Xp_out,
                                             (const cplx*)h_out, io.varn, (cplx*)Yp_out);
         count_launch();
     }

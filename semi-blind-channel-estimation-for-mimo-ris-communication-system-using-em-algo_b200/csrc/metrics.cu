@@ -88,8 +88,8 @@ __global__ void __launch_bounds__(256) k_after_iteration(Dims d, int l, const cp
         if (threadIdx.x == 0) lse[(size_t)b * d.itera + l] = a;
     }
     if (llf && Xd_true) {
-        const size_t pb = d.psi_shared ? 0 : b;
-        double rp = residual_sq(d, d.T_p, Yp + (size_t)b * d.T_p * d.n_rx, PsiP + pb * d.T_p * d.N1,
+        const size_t pb = d.psi_shared ? 0 : b, ppb = d.psiP_shared ? 0 : b;
+        double rp = residual_sq(d, d.T_p, Yp + (size_t)b * d.T_p * d.n_rx, PsiP + ppb * d.T_p * d.N1,
                                 Xp + (size_t)b * d.T_p * d.n_tx, th);
         rp = block_sum(rp, red);
         double rd = residual_sq(d, d.T_d, Yd + (size_t)b * d.T_d * d.n_rx, PsiD + pb * d.T_d * d.N1,

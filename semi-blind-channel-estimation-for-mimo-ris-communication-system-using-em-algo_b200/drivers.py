@@ -88,7 +88,8 @@ def run_point_device(cfg: SweepConfig, point_index: int, device=0, per_trial=Non
     # without the direct link every phase row is a RIS element: N rows instead of N + 1
     prob = engine.Problem(N=cfg.N if cfg.direct_link else cfg.N - 1, n_tx=cfg.n_tx, n_rx=cfg.n_rx, M=cfg.M, T_p=cfg.T_p,
                           T_d=cfg.T_d, itera=cfg.itera, mode=cfg.mode, genie_stop=cfg.genie_stop, quirks=cfg.quirks,
-                          zero_start=(cfg.start == "zero"), partition_r=cfg.partition_r)
+                          zero_start=(cfg.start == "zero"), partition_r=cfg.partition_r,
+                          psip_shared=True)      # the pilot design is deterministic: generated and stored once
     acc = PointResult()
     if hi <= lo:
         return acc

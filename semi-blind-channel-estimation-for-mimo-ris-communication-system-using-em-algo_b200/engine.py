@@ -17,7 +17,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import (FLAG_FULL_SCAN, FLAG_GENIE_STOP, FLAG_PSI_SHARED, FLAG_QUIRKS, FLAG_SUPERIMPOSED, FLAG_ZERO_START, MODE_HARD,
+from ._lib import (FLAG_FULL_SCAN, FLAG_GENIE_STOP, FLAG_PSIP_SHARED, FLAG_PSI_SHARED, FLAG_QUIRKS, FLAG_SUPERIMPOSED, FLAG_ZERO_START, MODE_HARD,
                    MODE_MMSE, MODE_PM, MODE_PM_BETA, MODE_SOFT, MODE_ZF)
 
 MODES = {"soft": MODE_SOFT, "hard": MODE_HARD, "pm": MODE_PM, "pm_beta": MODE_PM_BETA, "zf": MODE_ZF,
@@ -39,7 +39,8 @@ class Problem:
     genie_stop: bool = False
     quirks: bool = True
     zero_start: bool = False
-    psi_shared: bool = False
+    psi_shared: bool = False    # PsiP and PsiD are passed once ([T][N+1]) for the whole batch
+    psip_shared: bool = False   # only the (deterministic) pilot design PsiP is shared; data phases stay per trial
     partition_r: float = 0.0
     full_scan: bool = False   # E-step visits every tree node instead of skipping provably weightless subtrees
     superimposed: bool = False  # parallel protocol (Parallel/ParallelProtocol_Tp.py): Xp holds per-symbol offsets, T_p = 0
@@ -58,6 +59,7 @@ class Problem:
         flags |= FLAG_GENIE_STOP if self.genie_stop else 0
         flags |= FLAG_QUIRKS if self.quirks else 0
         flags |= FLAG_PSI_SHARED if self.psi_shared else 0
+        flags |= FLAG_PSIP_SHARED if self.psip_shared else 0
         flags |= FLAG_ZERO_START if self.zero_start else 0
         flags |= FLAG_FULL_SCAN if self.full_scan else 0
         flags |= FLAG_SUPERIMPOSED if self.superimposed else 0
@@ -69,8 +71,9 @@ class Problem:
 
     def shapes(self, B):
         pb = () if self.psi_shared else (B,)
+        ppb = () if (self.psi_shared or self.psip_shared) else (B,)
         return dict(Yd=(B, self.T_d, self.n_rx), Yp=(B, self.T_p, self.n_rx), PsiD=pb + (self.T_d, self.N + 1),
-                    PsiP=pb + (self.T_p, self.N + 1), Xp=(B, self.T_d if self.superimposed else self.T_p, self.n_tx),
+                    PsiP=ppb + (self.T_p, self.N + 1), Xp=(B, self.T_d if self.superimposed else self.T_p, self.n_tx),
                     theta0=(B, self.L, self.n_rx),
                     h_true=(B, self.L, self.n_rx), Xd_true=(B, self.T_d, self.n_tx))
 

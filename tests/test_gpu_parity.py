@@ -504,6 +504,41 @@ def test_shared_phase_design_across_batch(S, orc):
     assert relerr(shared.theta[1], ref) < RTOL
 
 
+def test_shared_pilot_design_only(S, orc):
+    """SBCE_FLAG_PSIP_SHARED: the deterministic pilot design is passed once, the random data phases per trial
+    (the layout of every `Proposed method/` sweep); must be bit-identical to the per-trial layout, on the host
+    route, the device route, the stand-alone M-step and the on-device generator + LS start."""
+    import dataclasses
+
+    import torch
+
+    N, n_tx, n_rx, M, T_p, T_d, itera, varn = 12, 4, 4, 16, 60, 48, 3, 0.3
+    B = 5
+    tb = S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn, B, seed=14, legacy=False, variant="top_tp")
+    assert np.array_equal(tb.PsiP[0], tb.PsiP[B - 1]) and not np.array_equal(tb.PsiD[0], tb.PsiD[1])
+    prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera)
+    full = S.run_host(prob, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, tb.varn, theta0=tb.theta0, h_true=tb.h, Xd_true=tb.Xd)
+    prob_s = dataclasses.replace(prob, psip_shared=True)
+    sh = S.run_host(prob_s, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP[0].copy(), tb.Xp, tb.varn, theta0=tb.theta0, h_true=tb.h,
+                    Xd_true=tb.Xd)
+    for k in ("theta", "kstar", "llf", "lse", "nmse"):
+        assert np.array_equal(getattr(full, k), getattr(sh, k)), k
+    ref = orc.em(tb.Yd[2], tb.Yp[2], tb.PsiD[2], tb.PsiP[2], tb.Xp[2], M, varn, itera, theta0=tb.theta0[2])
+    assert relerr(sh.theta[2], ref) < RTOL
+    # device route + generator + LS start with the shared pilot design
+    ses, ses_s = S.DeviceSession(prob, B), S.DeviceSession(prob_s, B)
+    g, gs = ses.generate(B, varn, seed=3, pilot_design="top"), ses_s.generate(B, varn, seed=3, pilot_design="top")
+    assert gs["PsiP"].shape == (T_p, N + 1) and torch.equal(g["PsiP"][3], gs["PsiP"])
+    for k in ("Yp", "Yd", "PsiD", "h", "Xp"):
+        assert torch.equal(g[k], gs[k]), k
+    t0, st = ses.ls_start(g["Yp"], g["PsiP"], g["Xp"])
+    t0s, sts = ses_s.ls_start(gs["Yp"], gs["PsiP"], gs["Xp"])
+    assert torch.equal(t0, t0s) and int(sts.abs().max()) == 0
+    r = ses.run(g["Yd"], g["Yp"], g["PsiD"], g["PsiP"], g["Xp"], g["varn"], theta0=t0, h_true=g["h"])
+    rs = ses_s.run(gs["Yd"], gs["Yp"], gs["PsiD"], gs["PsiP"], gs["Xp"], gs["varn"], theta0=t0s, h_true=gs["h"])
+    assert torch.equal(r.theta, rs.theta) and torch.equal(r.nmse, rs.nmse)
+
+
 def test_drivers_on_gpu_match_oracle_runner(S, orc):
     """The sweep drivers through the CUDA library equal the same drivers fed by the oracle."""
     import sys, os
