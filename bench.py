@@ -365,15 +365,15 @@ def run_ours(args):
             k["frac_hbm_peak"] = k["gbs"] / hbm_peak
         kernels[name] = k
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-    # (profiles/r01k_top_kernels_full.csv), valid for the default workload at 592 trials per launch
-    ncu_traffic = {"chol": 2.382261e9 + 590.672128e6, "gram": 0.578337e9 + 312.873984e6,
-                   "heff_qr": 0.177411e9 + 18.087168e6, "enum": 0.036424e9 + 8.273408e6}
+    # (profiles/r01m_top_kernels_full.csv), valid for the default workload at 1184 trials per launch
+    ncu_traffic = {"chol": 4.743103e9 + 1.170456e9, "gram": 1.129825e9 + 0.650163e9,
+                   "heff_qr": 0.355463e9 + 0.061982e9, "enum": 0.072850e9 + 0.055741e9}
     top = max((n for n in kernels if n in fm), key=lambda n: kernels[n]["ms_total"])
     roofline = dict(bound="tensor", pipe="FP64 tensor path (mma.sync DMMA; tcgen05 has no FP64 kind)", kernel=top, achieved=kernels[top]["tflops"], peak=fp64_peak, unit="TFLOP/s",
                     frac=kernels[top]["frac_fp64_peak"],
-                    # measured at 592 trials per launch; every kernel's traffic is linear in the trial count
-                    traffic=(ncu_traffic.get(top) * (B / 592.0) if (top in ncu_traffic and w == WORKLOAD) else None),
-                    traffic_unit="bytes per launch (ncu dram read+write, profiles/r01k_top_kernels_full.csv)",
+                    # measured at 1184 trials per launch; every kernel's traffic is linear in the trial count
+                    traffic=(ncu_traffic.get(top) * (B / 1184.0) if (top in ncu_traffic and w == WORKLOAD) else None),
+                    traffic_unit="bytes per launch (ncu dram read+write, profiles/r01m_top_kernels_full.csv)",
                     share_of_step=kernels[top]["share"],
                     peak_source="live DFMA micro-benchmark in libsbce (2 flop/FMA); MEASURED_PEAKS.json has no FP64 entry",
                     flops_per_launch=fm[top] * B,
