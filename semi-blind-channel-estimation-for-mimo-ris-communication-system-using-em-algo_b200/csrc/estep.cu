@@ -66,15 +66,24 @@ cudaError_t launch_pilot_stats(const Dims& d, int nb, const double* Xp, double* 
 template <int NTX, int NRX>
 __global__ void __launch_bounds__(128) k_heff_qr(Dims d, const cplx* __restrict__ Yd, const cplx* __restrict__ PsiD,
                                                  const cplx* __restrict__ theta, const int32_t* __restrict__ active,
-                                                 const cplx* __restrict__ Xoff, double* __restrict__ qr) {
+                                                 const cplx* __restrict__ Xoff, double* __restrict__ qr, int use_smem) {
     constexpr int NR = cmax(NTX, NRX);
+    extern __shared__ double2 heff_smem[];
     const int b = blockIdx.y;
     if (active != nullptr && active[b] == 0) return;
+    // theta of the trial is read by every lane at warp-uniform addresses, 16 values per RIS index: staged in
+    // shared memory once per CTA (coalesced) the inner loop issues LDS broadcasts instead of global loads
+    // (the global-load queue was the kernel's top stall, profiles/r01m); use_smem = 0: theta too long
+    const cplx* th = theta + (size_t)b * d.L * NRX;
+    if (use_smem) {
+        for (int e = threadIdx.x; e < d.L * NRX; e += blockDim.x) heff_smem[e] = th[e];
+        __syncthreads();
+        th = heff_smem;
+    }
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= d.T_d) return;
 
     const cplx* psi = PsiD + ((size_t)(d.psi_shared ? 0 : b) * d.T_d + t) * d.N1;
-    const cplx* th = theta + (size_t)b * d.L * NRX;
 
     cplx A[NR][NTX];
 #pragma unroll
@@ -90,7 +99,7 @@ __global__ void __launch_bounds__(128) k_heff_qr(Dims d, const cplx* __restrict_
 #pragma unroll
         for (int j = 0; j < NTX; ++j)
 #pragma unroll
-            for (int r = 0; r < NRX; ++r) cfma(A[r][j], p, __ldg(&row[j * NRX + r]));
+            for (int r = 0; r < NRX; ++r) cfma(A[r][j], p, row[j * NRX + r]);
     }
     cplx y[NR];
 #pragma unroll
@@ -590,10 +599,17 @@ __global__ void __launch_bounds__(WARPS * 32, (NTX > 4 ? 2 : 4)) k_enum(Dims d, 
     const int t = blockIdx.x * WARPS + warp;
     if (t >= d.T_d) return;
 
-    const double* rec = qr + ((size_t)b * d.T_d + t) * d.rec;
     double* ws = enum_smem + (size_t)warp * E::WS_DOUBLES;
     cplx* tab = (cplx*)(ws + E::O_TAB);
     double* g = ws + E::O_G;
+    // the QR record of the symbol: one coalesced load by the warp into the (still idle) flush scratch, then
+    // broadcast reads from shared memory (every lane needs all of it; 30+ uniform global loads per lane before)
+    const double* rec = ws + E::O_SCR;
+    {
+        const double* grec = qr + ((size_t)b * d.T_d + t) * d.rec;
+        for (int i = lane; i < d.rec; i += 32) ws[E::O_SCR + i] = grec[i];
+        __syncwarp();
+    }
     cplx yt[NTX];
     cplx r01 = mk(0.0, 0.0);
     double r00;
@@ -779,8 +795,15 @@ template <int NTX, int NRX>
 static cudaError_t run_heff(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
                             const int32_t* active, const double* Xoff, double* qr, cudaStream_t s) {
     dim3 grid((d.T_d + 127) / 128, nb);
-    k_heff_qr<NTX, NRX><<<grid, 128, 0, s>>>(d, (const cplx*)Yd, (const cplx*)PsiD, (const cplx*)theta, active,
-                                             (const cplx*)Xoff, qr);
+    size_t smem = sizeof(cplx) * (size_t)d.L * NRX;
+    const int use_smem = smem <= 64 * 1024;
+    if (!use_smem) smem = 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_heff_qr<NTX, NRX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_heff_qr<NTX, NRX><<<grid, 128, smem, s>>>(d, (const cplx*)Yd, (const cplx*)PsiD, (const cplx*)theta, active,
+                                                (const cplx*)Xoff, qr, use_smem);
     count_launch();
     return cudaGetLastError();
 }
