@@ -410,7 +410,8 @@ def run_ours(args):
                                         "weight (partial distance > incumbent + 64 varn^2) are skipped, outputs "
                                         "bit-identical to the full scan (see full_scan)",
                             l2="inputs (%.0f MB per GPU) larger than the 126 MB L2" % (input_bytes / 1e6), **w),
-                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(input_bytes), d2h_bytes_per_step=int(d2h_bytes),
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(input_bytes) * world,
+                         d2h_bytes_per_step=int(d2h_bytes) * world, bytes_are="whole job (all ranks)",
                          steps=e2e_steps, h2d_gbs_measured=h2d_gbs),
                 gpu_launches=int(launches), clocks=clocks, roofline=roofline, kernels=kernels, cpu_baseline=cpu,
                 full_scan=full,

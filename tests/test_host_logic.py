@@ -29,9 +29,25 @@ def test_library_exports_every_symbol_of_the_header():
     assert lib.sbce_error_string(-3).decode().startswith("unsupported")
 
 
+def test_python_constants_match_header():
+    """Every SBCE_MODE_* / SBCE_FLAG_* / SBCE_ST_* value of include/sbce.h equals its twin in _lib.py."""
+    header = open(os.path.join(ROOT, "include", "sbce.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+SBCE_((?:MODE|FLAG|ST|PILOTS|PHASES)_[A-Z_]+)\s+(\d+)u?", header)}
+    L = sbce._lib
+    for name, val in defs.items():
+        if name.startswith("PILOTS_"):
+            assert L.PILOTS[{"PILOTS_PM": "pm", "PILOTS_TOP": "top"}[name]] == val
+        elif name.startswith("PHASES_"):
+            assert L.PHASES_KIND[{"PHASES_RANDOM": "random", "PHASES_DFT": "dft"}[name]] == val
+        else:
+            assert getattr(L, name) == val, name
+    assert {"FLAG_SUPERIMPOSED", "FLAG_PSIP_SHARED", "MODE_MMSE", "ST_NOT_PD"} <= set(defs)
+
+
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(sbce._lib.Cfg) == 16 * 4
     assert ctypes.sizeof(sbce._lib.Io) == 16 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(sbce._lib.Gen) == 48 and sbce._lib.Gen.varh.offset == 24   # sbce_gen (checked against g++)
 
 
 def test_workspace_query_and_argument_errors_need_no_gpu():
