@@ -57,10 +57,20 @@ constexpr int RH_MAXR = 8;
 //   row Lp + r, column l = n*n_tx + i :  conj(B[l][r]) = sum_t psi[t,n] conj(m_t[i] y_t[r]),
 // one thread per column l with n_rx accumulators, plus the identity padding of the trapezoid.
 template <int NTX>
-__device__ __forceinline__ void gram_rhs_cta(const Dims& d, int T, int b, cplx* sPsi, cplx* sRr, const cplx* psi_b,
+__device__ __forceinline__ void gram_rhs_cta(const Dims& d, int T, int b, cplx* sPsi, cplx* /*unused*/, const cplx* psi_b,
                                              const cplx* __restrict__ Y, const cplx* __restrict__ sm, const cplx* Gi,
                                              cplx* Gb) {
     const int N1 = d.N1;
+    // Chunk length: as many symbols as the CTA's dynamic shared memory holds (the pair CTAs of the same launch
+    // size it for their operand ring).  profiles/r01m: with 16-symbol chunks this CTA -- one per trial, two
+    // barriers and a global-load round trip per chunk -- ran 2.6x longer than a pair CTA and held 23 % of the
+    // resident warp time while feeding the tensor pipe nothing; long chunks make it latency-cheap.
+    unsigned dyn_bytes;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+    const int per_sym = N1 + NTX * (d.n_rx > NTX ? d.n_rx : NTX);
+    int TCR = (int)(dyn_bytes / (sizeof(cplx) * per_sym));
+    TCR = max(1, min(TCR, 128));
+    cplx* sRr = sPsi + (size_t)TCR * N1;
     // ---------------- right-hand side rows + padding
     const int n_rx = d.n_rx, L = d.L;
     const cplx* m_b = sm + (size_t)b * T * NTX;
@@ -81,8 +91,8 @@ __device__ __forceinline__ void gram_rhs_cta(const Dims& d, int T, int b, cplx* 
         for (int u = 0; u < 2; ++u)
 #pragma unroll
             for (int r = 0; r < RH_MAXR; ++r) acc[u][r] = mk(0.0, 0.0);
-        for (int t0 = 0; t0 < T; t0 += GR_TC) {
-            const int tc = min(GR_TC, T - t0);
+        for (int t0 = 0; t0 < T; t0 += TCR) {
+            const int tc = min(TCR, T - t0);
             __syncthreads();
             for (int e = threadIdx.x; e < tc * N1; e += GR_THREADS) sPsi[e] = psi_b[(size_t)t0 * N1 + e];
             for (int e = threadIdx.x; e < tc * NTX * n_rx; e += GR_THREADS) {
