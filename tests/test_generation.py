@@ -246,3 +246,39 @@ def test_on_device_sweep_driver(S):
         assert abs(a["nmse"][i] - np.mean(nm)) <= 5e-5 * np.mean(nm)          # 4 significant figures
         assert a["ser"][i] == err / (cfg.monte_iter * T_d * cfg.n_tx)
         assert abs(a["ser_as_coded"][i] - coded / cfg.monte_iter) < 1e-12
+
+
+@gpu
+def test_baseline_json_configs_through_the_on_device_drivers(S):
+    """The sweep shapes BASELINE.json names beyond the bench line, end to end on the GPU (generation, LS start,
+    EM, accumulation) at a handful of trials: config 3 (`IRS_elements.py`: N = 16 ... 256, 2x2 QPSK, well-posed
+    T_p + T_d >= 1.3 L) and config 4 (`PMvsMLvsZFvsMMSE.py` / `SNR/all_Detectors.py`: 8x8 QPSK with the
+    exhaustive tree, 4x4 64-QAM with the PM partition p+1 = 2 -> 4096 candidates, SNR sweep, SER from hard decisions)."""
+    import math
+
+    # ---- config 3
+    for N in (16, 64, 256):
+        L = (N + 1) * 2
+        T_p = 20 * math.ceil(N / 15)
+        T_d = max(32, int(1.3 * L) - T_p + 8)
+        cfg = S.SweepConfig(N=N, n_tx=2, n_rx=2, M=4, T_p=T_p, T_d=T_d, itera=5, monte_iter=6, varn=1.0, mode="soft", seed=1,
+                            variant="top_tp", on_device=True)
+        r = S.nmse_vs_N(cfg, [N])
+        assert r["n_valid"][0] == 6 and np.isfinite(r["nmse"]).all() and r["nmse"][0] < 1.0, (N, r)
+    # ---- config 4: 8x8 QPSK, exhaustive 65536-leaf tree, hard decisions -> SER vs SNR
+    cfg = S.SweepConfig(N=16, n_tx=8, n_rx=8, M=4, T_p=160, T_d=64, itera=3, monte_iter=4, mode="hard", seed=2,
+                        variant="top_tp", on_device=True)
+    r = S.ser_vs_snr(cfg, [0.0, 10.0, 20.0])
+    assert np.isfinite(r["nmse"]).all() and (r["n_valid"] == 4).all()
+    assert r["nmse"][2] < r["nmse"][0] and r["ser"][2] <= r["ser"][0] and r["ser"][2] < 0.05
+    # ---- config 4: 4x4 64-QAM with the partition (p = int(6 / log2 64) = 1 -> 64^2 = 4096 candidates per symbol)
+    cfg = S.SweepConfig(N=16, n_tx=4, n_rx=4, M=64, T_p=80, T_d=48, itera=2, monte_iter=4, mode="pm_beta", partition_r=6,
+                        quirks=False, seed=3, variant="top_tp", on_device=True)
+    r = S.nmse_vs_snr(cfg, [10.0, 30.0])
+    assert np.isfinite(r["nmse"]).all() and r["nmse"][1] < r["nmse"][0]
+    # ---- config 5 shape at toy trial count: 8x8 16-QAM, partitioned (2^32 joint hypotheses are out of reach
+    # of any exhaustive method), N = 32
+    cfg = S.SweepConfig(N=32, n_tx=8, n_rx=8, M=16, T_p=320, T_d=32, itera=2, monte_iter=3, mode="pm_beta", partition_r=4,
+                        quirks=False, seed=4, variant="top_tp", on_device=True)
+    r = S.nmse_vs_snr(cfg, [20.0])
+    assert np.isfinite(r["nmse"]).all() and r["n_valid"][0] == 3
