@@ -305,7 +305,7 @@ def run_ours(args):
         engine.run_host(prob, pin["Yd"], pin["Yp"], pin["PsiD"], pin["PsiP"], pin["Xp"], varn_pin,
                         theta0=pin["theta0"], h_true=pin["h_true"], device=local, out=hout)
 
-    e2e_steps = max(1, min(args.steps, 8))
+    e2e_steps = max(args.steps, 24)   # >= 24 synchronous calls (~1.6 s): a sporadic slow call moves the mean by < 5 %
     # warm-up: pool allocation and >= 1.5 s of steady calls.  On this pool's VM hosts single calls sporadically take
     # 1.5-2x longer for ~0.3 s at a time (SM clock 1965 MHz and the 55 GB/s copy rate unchanged, no relation to the
     # amount of warm-up; the device-timed `value` queues its kernels ahead and does not see it): e2e.value is the
