@@ -180,6 +180,31 @@ def case_hard_llf(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn):
     _save(name, meta, d)
 
 
+def case_loglik(name, seed, N, n_rx, M, T_p, T_d, itera, varn):
+    """`Proposed method/Log_likelihood.py` (named in BASELINE.json north_star): hard EM + as-coded LLF with Z_d and
+    n_tx as arguments (:45-85), on the script's own data (:156-166: pilot phases exp(-j2pi t n/N) over all N+1 rows).
+    n_tx = 1 only: the script sizes its weight matrix with `M^n_tx` (XOR, quirk Q9), which holds K rows only then."""
+    n_tx = 1
+    ns = rh.load_functions("Proposed method/Log_likelihood.py", N=N, n_tx=n_tx, n_rx=n_rx, beta_max=TWO_PI)
+    np.random.seed(seed)
+    with rh.quiet():
+        h = ns["channelMatrix"](n_tx, n_rx, N, 1)
+        X_d, aps = ns["symbols"](n_tx, M, T_d)
+        PsiTilde_tp, PsiTilde_td = ns["irsMatrix"](T_p, T_d, N, 0, 1)
+        PsiTilde_td = np.insert(PsiTilde_td, 0, np.ones((1, T_d), dtype="complex128"), axis=0)
+        X_p = ns["pilotSymbols"](n_tx, M, T_p)
+        Y_p, Y_d, Z_p, Z_d, h_initial = ns["receivedSignals"](T_p, T_d, PsiTilde_tp, PsiTilde_td, n_rx, n_tx, X_d, X_p, h,
+                                                              varn, M, N)
+        theta, llf = ns["em"](Y_d, Y_p, T_d, T_p, Z_p, Z_d, PsiTilde_td, aps, M, varn, itera, h_initial, n_tx)
+    d = rh.extract_arrays(Y_p, Y_d, Z_p, X_p, X_d, PsiTilde_tp, PsiTilde_td, h, h_initial, n_tx, n_rx)
+    L = (N + 1) * n_tx
+    meta = dict(kind="loglik", seed=seed, N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera, varn=varn,
+                src="Proposed method/Log_likelihood.py:em")
+    d.update(theta_ref=np.asarray(theta, dtype=np.complex128).reshape(L, n_rx), nmse_ref=_nmse(theta, h),
+             llf_ref=np.asarray(llf, dtype=np.float64).reshape(-1))
+    _save(name, meta, d)
+
+
 def case_hard_ser(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn):
     """Hard EM returning last-iteration decisions + as-coded SER:
     `Proposed method/SER/log_max_SER.py:51-89,162`."""
@@ -348,6 +373,8 @@ def main(argv):
         case_parallel("parallel_1x4_s51", 51, 5, 1, 4, 16, 8, 24, 4, 0.1)
     if want("parallel_2x2_s52"):
         case_parallel("parallel_2x2_s52", 52, 4, 2, 2, 4, 30, 20, 3, 0.2)
+    if want("loglik_s61"):
+        case_loglik("loglik_s61", 61, 6, 4, 4, 10, 24, 4, 0.1)
     if want("script_top_td_s0"):
         case_script("script_top_td_s0", "Proposed_method_NMSEvsTd.py", 0)
     if want("script_top_tp_s0"):

@@ -161,6 +161,12 @@ def em_llf(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, all_possibleSymbols, M, varn, i
     return res.theta.reshape(-1, 1), res.llf.reshape(int(itera), 1)
 
 
+def em_loglik(Y_d, Y_p, T_d, T_p, Z_p, Z_d, PsiTilde_td, all_possibleSymbols, M, varn, itera, h_initial, n_tx=None, **kw):
+    """`Proposed method/Log_likelihood.py:45` -- the same estimator as em_llf with the positional signature of that
+    script (Z_d and n_tx are arguments there instead of module globals).  Returns (theta, logLikelihood (itera,1))."""
+    return em_llf(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, all_possibleSymbols, M, varn, itera, h_initial, Z_d=Z_d, **kw)
+
+
 def em_ser(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, all_possibleSymbols, M, varn, itera, h_initial, **kw):
     """Hard-decision EM returning (theta, X_dest): X_dest is the list of (1,n_tx) decisions
     of the last iteration, made before its M-step (SER/log_max_SER.py:77-78,89)."""

@@ -298,6 +298,22 @@ def test_em_hard_golden(S, orc, name):
     assert relerr(theta.reshape(g["theta_ref"].shape), g["theta_ref"]) < RTOL
 
 
+@pytest.mark.parametrize("name", golden_names("loglik"))
+def test_em_loglik_golden(S, orc, name):
+    """`Proposed method/Log_likelihood.py:45` through its own positional signature (Z_d, n_tx as arguments)."""
+    meta, g = load_golden(name)
+    n_tx, n_rx, M = int(meta["n_tx"]), int(meta["n_rx"]), int(meta["M"])
+    T_d, T_p, varn, itera = int(meta["T_d"]), int(meta["T_p"]), float(meta["varn"]), int(meta["itera"])
+    Y_d, Y_p, Z_p, PsiTilde_td = _ref_objects(g, n_rx)
+    Wd = (g["PsiD"][:, :, None] * g["Xd"][:, None, :]).reshape(T_d, -1)
+    Z_d = [np.kron(Wd[t][None, :], np.eye(n_rx, dtype=np.complex128)) for t in range(T_d)]
+    table = orc.hypothesis_table(orc.qam_constellation(M), n_tx)
+    theta, llf = S.em_loglik(Y_d, Y_p, T_d, T_p, Z_p, Z_d, PsiTilde_td, table, M, varn, itera, g["theta0"].reshape(-1, 1), n_tx)
+    assert llf.shape == (itera, 1)
+    np.testing.assert_allclose(llf.reshape(-1), g["llf_ref"], rtol=1e-9)
+    assert relerr(theta.reshape(g["theta_ref"].shape), g["theta_ref"]) < RTOL
+
+
 @pytest.mark.parametrize("name", golden_names("multi"))
 def test_multi_detector_golden(S, orc, name):
     meta, g = load_golden(name)

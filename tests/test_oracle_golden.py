@@ -78,6 +78,16 @@ def test_superimposed_pilots_match_reference(name):
     assert abs(orc.nmse(th, g["h"]) - g["nmse_ref"]) <= 1e-9 * max(1.0, g["nmse_ref"])
 
 
+@pytest.mark.parametrize("name", golden_names("loglik"))
+def test_log_likelihood_script_matches_reference(name):
+    """`Proposed method/Log_likelihood.py` (the convergence curve named in BASELINE.json): hard EM + as-coded LLF."""
+    meta, g = load_golden(name)
+    th, tr = orc.em(g["Yd"], g["Yp"], g["PsiD"], g["PsiP"], g["Xp"], int(meta["M"]), float(meta["varn"]),
+                    int(meta["itera"]), theta0=g["theta0"], hard=True, Xd_true=g["Xd"], return_trace=True)
+    assert relerr(th, g["theta_ref"]) < RTOL_THETA
+    np.testing.assert_allclose(np.array(tr["llf"]), g["llf_ref"], rtol=1e-11)
+
+
 def test_known_answers_of_baseline_md():
     """BASELINE.md section 3.2 row 3 (seed 1234)."""
     meta, g = load_golden("soft_rev4_s1234")
