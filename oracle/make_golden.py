@@ -205,6 +205,30 @@ def case_loglik(name, seed, N, n_rx, M, T_p, T_d, itera, varn):
     _save(name, meta, d)
 
 
+def case_irs_elements(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn):
+    """BASELINE.json config 3: `Proposed method/IRS_elements.py` em (:268-304: soft EM from the LS start with the
+    trailing N argument, multiprecision weights, genie stop on the global h) on the driver's own data
+    (:380-398: pilots and data symbols drawn once, then per N: channel, phases, ones row, received blocks)."""
+    ns = rh.load_functions("Proposed method/IRS_elements.py", n_tx=n_tx, n_rx=n_rx, beta_max=TWO_PI)
+    np.random.seed(seed)
+    with rh.quiet():
+        X_p = ns["pilotSymbols"](n_tx, M, T_p)
+        X_d, aps, _cons = ns["symbols"](n_tx, M, T_d)
+        h = ns["channelMatrix"](n_tx, n_rx, N, 1)
+        PsiTilde_tp, PsiTilde_td = ns["irsMatrix"](T_p, T_d, N, 0, 1)
+        PsiTilde_td = np.insert(PsiTilde_td, 0, np.ones((1, T_d), dtype="complex128"), axis=0)
+        Y_p, Y_d, Z_p, Z_d, h_initial = ns["receivedSignals"](T_p, T_d, PsiTilde_tp, PsiTilde_td, n_rx, n_tx, X_d, X_p, h,
+                                                              varn, M)
+        ns["h"] = h
+        theta = ns["em"](Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, aps, M, varn, itera, h_initial, N)
+    d = rh.extract_arrays(Y_p, Y_d, Z_p, X_p, X_d, PsiTilde_tp, PsiTilde_td, h, h_initial, n_tx, n_rx)
+    L = (N + 1) * n_tx
+    meta = dict(kind="irs", seed=seed, N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera, varn=varn,
+                src="Proposed method/IRS_elements.py:em")
+    d.update(theta_ref=np.asarray(theta, dtype=np.complex128).reshape(L, n_rx), nmse_ref=_nmse(theta, h))
+    _save(name, meta, d)
+
+
 def case_hard_ser(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn):
     """Hard EM returning last-iteration decisions + as-coded SER:
     `Proposed method/SER/log_max_SER.py:51-89,162`."""
@@ -373,6 +397,8 @@ def main(argv):
         case_parallel("parallel_1x4_s51", 51, 5, 1, 4, 16, 8, 24, 4, 0.1)
     if want("parallel_2x2_s52"):
         case_parallel("parallel_2x2_s52", 52, 4, 2, 2, 4, 30, 20, 3, 0.2)
+    if want("irs_elements_s71"):
+        case_irs_elements("irs_elements_s71", 71, 7, 2, 2, 4, 20, 24, 5, 1.0)
     if want("loglik_s61"):
         case_loglik("loglik_s61", 61, 6, 4, 4, 10, 24, 4, 0.1)
     if want("script_top_td_s0"):

@@ -314,6 +314,18 @@ def test_em_loglik_golden(S, orc, name):
     assert relerr(theta.reshape(g["theta_ref"].shape), g["theta_ref"]) < RTOL
 
 
+@pytest.mark.parametrize("name", golden_names("irs"))
+def test_em_irs_elements_golden(S, orc, name):
+    """BASELINE.json config 3: `Proposed method/IRS_elements.py:268` em(..., h_initial, N) with its genie stop."""
+    meta, g = load_golden(name)
+    n_tx, n_rx, M, N = int(meta["n_tx"]), int(meta["n_rx"]), int(meta["M"]), int(meta["N"])
+    Y_d, Y_p, Z_p, PsiTilde_td = _ref_objects(g, n_rx)
+    table = orc.hypothesis_table(orc.qam_constellation(M), n_tx)
+    theta = S.em(Y_d, Y_p, int(meta["T_d"]), int(meta["T_p"]), Z_p, PsiTilde_td, table, M, float(meta["varn"]),
+                 int(meta["itera"]), g["theta0"].reshape(-1, 1), N, h=g["h"], genie_stop=True)
+    assert relerr(theta.reshape(g["theta_ref"].shape), g["theta_ref"]) < RTOL
+
+
 @pytest.mark.parametrize("name", golden_names("multi"))
 def test_multi_detector_golden(S, orc, name):
     meta, g = load_golden(name)

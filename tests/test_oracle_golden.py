@@ -88,6 +88,15 @@ def test_log_likelihood_script_matches_reference(name):
     np.testing.assert_allclose(np.array(tr["llf"]), g["llf_ref"], rtol=1e-11)
 
 
+@pytest.mark.parametrize("name", golden_names("irs"))
+def test_irs_elements_script_matches_reference(name):
+    """BASELINE.json config 3, `Proposed method/IRS_elements.py` em: soft EM, LS start, genie stop."""
+    meta, g = load_golden(name)
+    th = orc.em(g["Yd"], g["Yp"], g["PsiD"], g["PsiP"], g["Xp"], int(meta["M"]), float(meta["varn"]), int(meta["itera"]),
+                theta0=g["theta0"], h_true=g["h"], genie_stop=True)
+    assert relerr(th, g["theta_ref"]) < RTOL_THETA
+
+
 def test_known_answers_of_baseline_md():
     """BASELINE.md section 3.2 row 3 (seed 1234)."""
     meta, g = load_golden("soft_rev4_s1234")
