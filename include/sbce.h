@@ -74,6 +74,9 @@ extern "C" {
                                    Proposed_method_NMSEvsTp.py:77) while its data phases are redrawn per trial (PM.py:125-129):
                                    passing the pilot design once halves the input volume of a sweep point */
 
+#define SBCE_FLAG_ZF_STOP_GUARD 128u /* ZF mode: the genie stop also requires l != 0, as em_zf of
+                                   "Proposed method/all_detectorsvsTd.py":127 has it (PMvsMLvsZFvsMMSE.py:128 does not) */
+
 /* per-trial status bits */
 #define SBCE_ST_NOT_PD 1    /* non-positive pivot in the Cholesky of the normal matrix (singular M-step) */
 #define SBCE_ST_NONFINITE 2 /* a non-finite value appeared in theta                                      */

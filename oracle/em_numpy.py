@@ -541,9 +541,10 @@ def detector_stats(Yd, PsiD, Theta, cons, n_tx, varn, kind, quirks=True):
 
 
 def em_detector(Yd, Yp, PsiD, PsiP, Xp, M, varn, itera, theta0, kind="zf", h_true=None, genie_stop=True,
-                quirks=True, return_trace=False):
+                quirks=True, return_trace=False, zf_stop_guard=False):
     """`em_zf` (`PMvsMLvsZFvsMMSE.py:95-133`) / `em_mmse` (:54-93).  NOTE the genie stop of em_zf has no
-    `l != 0` guard (:128) while em_mmse's has (:87)."""
+    `l != 0` guard (:128) while em_mmse's has (:87); `all_detectorsvsTd.py:127` has the guard in em_zf too
+    (zf_stop_guard=True) and `SNR/all_Detectors.py` has no stop in em / em_ml / em_zf / em_mmse (genie_stop=False)."""
     n_tx = Xp.shape[1]
     cons = qam_constellation(M)
     Theta = np.array(theta0, dtype=np.complex128)
@@ -555,7 +556,7 @@ def em_detector(Yd, Yp, PsiD, PsiP, Xp, M, varn, itera, theta0, kind="zf", h_tru
         Gd, Bd = gram_and_rhs(PsiD, Yd, m, R)
         Theta = solve_normal(Gp + Gd, Bp + Bd)
         iters = l + 1
-        if genie_stop and h_true is not None and (l != 0 or kind == "zf") \
+        if genie_stop and h_true is not None and (l != 0 or (kind == "zf" and not zf_stop_guard)) \
                 and abs(np.linalg.norm(Theta) - np.linalg.norm(h_true)) < 1:
             break
     return (Theta, dict(iters=iters)) if return_trace else Theta

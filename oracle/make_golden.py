@@ -281,10 +281,12 @@ def case_pm(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn, partition_r, we
     _save(name, meta, d)
 
 
-def case_multi(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn, partition_r):
+def case_multi(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn, partition_r,
+               script="Proposed method/PMvsMLvsZFvsMMSE.py"):
     """`Proposed method/PMvsMLvsZFvsMMSE.py`: em / em_ml / em_pm with the genie stop
-    active (needs the module global h), same inputs for all (:54-292)."""
-    ns = rh.load_functions("Proposed method/PMvsMLvsZFvsMMSE.py", N=N, n_tx=n_tx, n_rx=n_rx, beta_max=TWO_PI)
+    active (needs the module global h), same inputs for all (:54-292).  The same five estimators ship again in
+    `Proposed method/all_detectorsvsTd.py` and `Proposed method/SNR/all_Detectors.py` (BASELINE.json config 4)."""
+    ns = rh.load_functions(script, N=N, n_tx=n_tx, n_rx=n_rx, beta_max=TWO_PI)
     np.random.seed(seed)
     out = {}
     with rh.quiet():
@@ -306,7 +308,7 @@ def case_multi(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn, partition_r)
     d = _dense(g, n_tx, n_rx)
     L = (N + 1) * n_tx
     meta = dict(kind="multi", order="multi", variant="pm", seed=seed, N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d,
-                itera=itera, varn=varn, partition_r=partition_r, src="Proposed method/PMvsMLvsZFvsMMSE.py")
+                itera=itera, varn=varn, partition_r=partition_r, src=script)
     for k, v in out.items():
         d[k + "_ref"] = np.asarray(v, dtype=np.complex128).reshape(L, n_rx)
         d["nmse_" + k[6:] + "_ref"] = _nmse(v, h)
@@ -383,6 +385,11 @@ def main(argv):
         case_pm("pm_beta_3x3_s13", 13, 4, 3, 3, 4, 24, 16, 3, 0.5, 2, True)
     if want("multi_s3"):
         case_multi("multi_s3", 3, 8, 2, 2, 4, 12, 40, 3, 0.1, 1)
+    if want("multi_td_s4"):
+        case_multi("multi_td_s4", 4, 6, 2, 2, 4, 10, 24, 3, 0.2, 1, script="Proposed method/all_detectorsvsTd.py")
+    if want("multi_snr_s5"):
+        case_multi("multi_snr_s5", 5, 6, 2, 2, 4, 10, 24, 3, 10.0 / 10 ** (12 / 10.0), 1,
+                   script="Proposed method/SNR/all_Detectors.py")
     if want("det_16qam_s31"):
         case_detectors("det_16qam_s31", 31, 6, 2, 2, 16, 6, 24, 4, 0.3)
     if want("det_3x3_s32"):

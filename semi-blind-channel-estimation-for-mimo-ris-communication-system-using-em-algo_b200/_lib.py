@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libsbce.so")
 MODE_SOFT, MODE_HARD, MODE_PM, MODE_PM_BETA, MODE_ZF, MODE_MMSE = 0, 1, 2, 3, 4, 5
 FLAG_GENIE_STOP, FLAG_QUIRKS, FLAG_PSI_SHARED, FLAG_ZERO_START, FLAG_FULL_SCAN, FLAG_SUPERIMPOSED = 1, 2, 4, 8, 16, 32
 FLAG_PSIP_SHARED = 64
+FLAG_ZF_STOP_GUARD = 128
 ST_NOT_PD, ST_NONFINITE = 1, 2
 
 

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) k_after_iteration(Dims d, int l, const cp
         a = block_sum(a, red);
         c = block_sum(c, red);
         // em_zf's stop has no `l != 0` guard (PMvsMLvsZFvsMMSE.py:128); every other estimator's has
-        const bool guard_ok = (l != 0) || (d.mode == SBCE_MODE_ZF);
+        const bool guard_ok = (l != 0) || (d.mode == SBCE_MODE_ZF && !(d.flags & SBCE_FLAG_ZF_STOP_GUARD));
         if (threadIdx.x == 0 && guard_ok && fabs(sqrt(a) - sqrt(c)) < 1.0) active[b] = 0;
     }
 }

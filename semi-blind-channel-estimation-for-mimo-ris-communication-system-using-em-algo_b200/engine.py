@@ -17,7 +17,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import (FLAG_FULL_SCAN, FLAG_GENIE_STOP, FLAG_PSIP_SHARED, FLAG_PSI_SHARED, FLAG_QUIRKS, FLAG_SUPERIMPOSED, FLAG_ZERO_START, MODE_HARD,
+from ._lib import (FLAG_FULL_SCAN, FLAG_GENIE_STOP, FLAG_PSIP_SHARED, FLAG_PSI_SHARED, FLAG_ZF_STOP_GUARD, FLAG_QUIRKS, FLAG_SUPERIMPOSED, FLAG_ZERO_START, MODE_HARD,
                    MODE_MMSE, MODE_PM, MODE_PM_BETA, MODE_SOFT, MODE_ZF)
 
 MODES = {"soft": MODE_SOFT, "hard": MODE_HARD, "pm": MODE_PM, "pm_beta": MODE_PM_BETA, "zf": MODE_ZF,
@@ -43,6 +43,7 @@ class Problem:
     psip_shared: bool = False   # only the (deterministic) pilot design PsiP is shared; data phases stay per trial
     partition_r: float = 0.0
     full_scan: bool = False   # E-step visits every tree node instead of skipping provably weightless subtrees
+    zf_stop_guard: bool = False  # ZF mode: genie stop only from the second iteration on (all_detectorsvsTd.py:127)
     superimposed: bool = False  # parallel protocol (Parallel/ParallelProtocol_Tp.py): Xp holds per-symbol offsets, T_p = 0
 
     @property
@@ -63,6 +64,7 @@ class Problem:
         flags |= FLAG_ZERO_START if self.zero_start else 0
         flags |= FLAG_FULL_SCAN if self.full_scan else 0
         flags |= FLAG_SUPERIMPOSED if self.superimposed else 0
+        flags |= FLAG_ZF_STOP_GUARD if self.zf_stop_guard else 0
         c = _lib.Cfg()
         c.N, c.n_tx, c.n_rx, c.M = self.N, self.n_tx, self.n_rx, self.M
         c.T_p, c.T_d, c.itera, c.batch = self.T_p, self.T_d, self.itera, batch

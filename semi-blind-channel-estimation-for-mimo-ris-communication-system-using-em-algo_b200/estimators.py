@@ -68,14 +68,15 @@ def _theta_arg(h_initial, L, n_rx):
 
 
 def _run(mode, Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, M, varn, itera, h_initial, n_tx, *, cons=None, h=None,
-         genie_stop=False, Xd_true=None, partition_r=0.0, quirks=True, PsiTilde_tp=None, X_p=None, device=0):
+         genie_stop=False, Xd_true=None, partition_r=0.0, quirks=True, PsiTilde_tp=None, X_p=None, device=0,
+         zf_stop_guard=False):
     Yd, Yp, PsiD, PsiP, Xp, n_rx, N1 = _common(Y_d, Y_p, Z_p, PsiTilde_td, M, n_tx, PsiTilde_tp, X_p, cons)
     if Yd.shape[0] != T_d or Yp.shape[0] != T_p:
         raise ValueError("T_d / T_p do not match the lengths of Y_d / Y_p")
     L = N1 * n_tx
     prob = engine.Problem(N=N1 - 1, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=int(itera), mode=mode,
                           genie_stop=bool(genie_stop and h is not None), quirks=quirks,
-                          zero_start=h_initial is None, partition_r=partition_r)
+                          zero_start=h_initial is None, partition_r=partition_r, zf_stop_guard=zf_stop_guard)
     h_true = None if h is None else np.asarray(h, dtype=np.complex128).reshape(1, L, n_rx)
     xd = None if Xd_true is None else np.asarray(Xd_true, dtype=np.complex128).reshape(1, T_d, n_tx)
     res = engine.run_host(prob, Yd[None], Yp[None], PsiD[None], PsiP[None], Xp[None], float(varn),
@@ -195,8 +196,10 @@ def em_pm_beta(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, M, varn, itera, h_initial, 
 
 def em_zf(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, all_possibleSymbols, M, varn, itera, h_initial, h, *,
           genie_stop=True, quirks=True, **kw):
-    """Zero-forcing detector EM (PMvsMLvsZFvsMMSE.py:95-133).  quirks=True reproduces the off-by-one psi slice,
-    the table-indexing slicer and the genie stop without the `l != 0` guard."""
+    """Zero-forcing detector EM (PMvsMLvsZFvsMMSE.py:95-133).  quirks=True reproduces the off-by-one psi slice and
+    the table-indexing slicer.  The three scripts that ship this function differ only in the genie stop:
+    PMvsMLvsZFvsMMSE.py:128 stops without the `l != 0` guard (default here), all_detectorsvsTd.py:127 has the
+    guard (`zf_stop_guard=True`), SNR/all_Detectors.py has no stop at all (`genie_stop=False`)."""
     n_tx = _ntx_from_table(all_possibleSymbols)
     cons = constellation_from_table(all_possibleSymbols, M)
     res, _ = _run("zf", Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, M, varn, itera, h_initial, n_tx, cons=cons, h=h,
