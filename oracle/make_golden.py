@@ -229,6 +229,52 @@ def case_irs_elements(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn):
     _save(name, meta, d)
 
 
+def case_soft_td(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn):
+    """`Proposed method/Proposed_method_NMSEvsTd.py` em (:44-76) in its driver's order (:141-150: channel, pilots,
+    then per T_d symbols, phases, ones row, received blocks)."""
+    ns = rh.load_functions("Proposed method/Proposed_method_NMSEvsTd.py", N=N, n_tx=n_tx, n_rx=n_rx, beta_max=TWO_PI)
+    np.random.seed(seed)
+    with rh.quiet():
+        h = ns["channelMatrix"](n_tx, n_rx, N, 1)
+        X_p = ns["pilotSymbols"](n_tx, M, T_p)
+        X_d, aps = ns["symbols"](n_tx, M, T_d)
+        PsiTilde_tp, PsiTilde_td = ns["irsMatrix"](T_p, T_d, N, 0, 1)
+        PsiTilde_td = np.insert(PsiTilde_td, 0, np.ones((1, T_d), dtype="complex128"), axis=0)
+        Y_p, Y_d, Z_p, Z_d, h_initial = ns["receivedSignals"](T_p, T_d, PsiTilde_tp, PsiTilde_td, n_rx, n_tx, X_d, X_p, h,
+                                                              varn, M)
+        theta = ns["em"](Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, aps, M, varn, itera, h_initial)
+    d = rh.extract_arrays(Y_p, Y_d, Z_p, X_p, X_d, PsiTilde_tp, PsiTilde_td, h, h_initial, n_tx, n_rx)
+    L = (N + 1) * n_tx
+    meta = dict(kind="soft_td", seed=seed, N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera, varn=varn,
+                src="Proposed method/Proposed_method_NMSEvsTd.py:em")
+    d.update(theta_ref=np.asarray(theta, dtype=np.complex128).reshape(L, n_rx), nmse_ref=_nmse(theta, h))
+    _save(name, meta, d)
+
+
+def case_iterations_llf(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn):
+    """`Proposed method/IterationsvsLLF.py` em (:44-84: SOFT EM + as-coded LLF, Z_d and n_tx as arguments) on the
+    script's own data (:141-150: pilot phases exp(-j2pi t n/N) over N rows plus an inserted ones row)."""
+    ns = rh.load_functions("Proposed method/IterationsvsLLF.py", N=N, n_tx=n_tx, n_rx=n_rx, beta_max=TWO_PI)
+    np.random.seed(seed)
+    with rh.quiet():
+        h = ns["channelMatrix"](n_tx, n_rx, N, 1)
+        X_d, aps = ns["symbols"](n_tx, M, T_d)
+        PsiTilde_tp, PsiTilde_td = ns["irsMatrix"](T_p, T_d, N, 0, 1)
+        PsiTilde_tp = np.insert(PsiTilde_tp, 0, np.ones((1, T_p), dtype="complex128"), axis=0)
+        PsiTilde_td = np.insert(PsiTilde_td, 0, np.ones((1, T_d), dtype="complex128"), axis=0)
+        X_p = ns["pilotSymbols"](n_tx, M, T_p)
+        Y_p, Y_d, Z_p, Z_d, h_initial = ns["receivedSignals"](T_p, T_d, PsiTilde_tp, PsiTilde_td, n_rx, n_tx, X_d, X_p, h,
+                                                              varn, M, N)
+        theta, llf = ns["em"](Y_d, Y_p, T_d, T_p, Z_p, Z_d, PsiTilde_td, aps, M, varn, itera, h_initial, n_tx)
+    d = rh.extract_arrays(Y_p, Y_d, Z_p, X_p, X_d, PsiTilde_tp, PsiTilde_td, h, h_initial, n_tx, n_rx)
+    L = (N + 1) * n_tx
+    meta = dict(kind="iter_llf", seed=seed, N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera, varn=varn,
+                src="Proposed method/IterationsvsLLF.py:em")
+    d.update(theta_ref=np.asarray(theta, dtype=np.complex128).reshape(L, n_rx), nmse_ref=_nmse(theta, h),
+             llf_ref=np.asarray(llf, dtype=np.float64).reshape(-1))
+    _save(name, meta, d)
+
+
 def case_hard_ser(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn):
     """Hard EM returning last-iteration decisions + as-coded SER:
     `Proposed method/SER/log_max_SER.py:51-89,162`."""
@@ -404,6 +450,10 @@ def main(argv):
         case_parallel("parallel_1x4_s51", 51, 5, 1, 4, 16, 8, 24, 4, 0.1)
     if want("parallel_2x2_s52"):
         case_parallel("parallel_2x2_s52", 52, 4, 2, 2, 4, 30, 20, 3, 0.2)
+    if want("soft_td_s81"):
+        case_soft_td("soft_td_s81", 81, 6, 2, 2, 4, 12, 28, 3, 0.1)
+    if want("iter_llf_s82"):
+        case_iterations_llf("iter_llf_s82", 82, 6, 2, 2, 4, 12, 24, 4, 0.1)
     if want("irs_elements_s71"):
         case_irs_elements("irs_elements_s71", 71, 7, 2, 2, 4, 20, 24, 5, 1.0)
     if want("loglik_s61"):

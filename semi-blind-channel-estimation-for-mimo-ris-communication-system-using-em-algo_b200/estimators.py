@@ -145,8 +145,8 @@ def _true_data_from_Zd(Z_d, PsiTilde_td, n_rx, n_tx):
 
 
 def em_llf(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, all_possibleSymbols, M, varn, itera, h_initial, *, Z_d=None,
-           X_d=None, **kw):
-    """Hard-decision EM returning (theta, logLikelihood (itera,1)) -- the LLF exactly as
+           X_d=None, soft=False, **kw):
+    """Hard-decision (soft=True: soft-decision) EM returning (theta, logLikelihood (itera,1)) -- the LLF exactly as
     coded in ML_detecctor.py:84 (needs the TRUE data: Z_d list or X_d list)."""
     n_tx = _ntx_from_table(all_possibleSymbols)
     cons = constellation_from_table(all_possibleSymbols, M)
@@ -157,8 +157,8 @@ def em_llf(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, all_possibleSymbols, M, varn, i
         xd = _true_data_from_Zd(Z_d, PsiTilde_td, n_rx, n_tx)
     else:
         raise ValueError("em_llf needs Z_d or X_d (the reference reads Z_d from a module global)")
-    res, _ = _run("hard", Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, M, varn, itera, h_initial, n_tx, cons=cons,
-                  Xd_true=xd, **kw)
+    res, _ = _run("soft" if soft else "hard", Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, M, varn, itera, h_initial, n_tx,
+                  cons=cons, Xd_true=xd, **kw)
     return res.theta.reshape(-1, 1), res.llf.reshape(int(itera), 1)
 
 
@@ -166,6 +166,14 @@ def em_loglik(Y_d, Y_p, T_d, T_p, Z_p, Z_d, PsiTilde_td, all_possibleSymbols, M,
     """`Proposed method/Log_likelihood.py:45` -- the same estimator as em_llf with the positional signature of that
     script (Z_d and n_tx are arguments there instead of module globals).  Returns (theta, logLikelihood (itera,1))."""
     return em_llf(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, all_possibleSymbols, M, varn, itera, h_initial, Z_d=Z_d, **kw)
+
+
+def em_iterations_llf(Y_d, Y_p, T_d, T_p, Z_p, Z_d, PsiTilde_td, all_possibleSymbols, M, varn, itera, h_initial, n_tx=None,
+                      **kw):
+    """`Proposed method/IterationsvsLLF.py:44` -- SOFT-decision EM with the as-coded LLF per iteration, positional
+    signature of that script.  Returns (theta, logLikelihood (itera,1))."""
+    return em_llf(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, all_possibleSymbols, M, varn, itera, h_initial, Z_d=Z_d, soft=True,
+                  **kw)
 
 
 def em_ser(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, all_possibleSymbols, M, varn, itera, h_initial, **kw):

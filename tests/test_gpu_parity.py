@@ -314,6 +314,25 @@ def test_em_loglik_golden(S, orc, name):
     assert relerr(theta.reshape(g["theta_ref"].shape), g["theta_ref"]) < RTOL
 
 
+@pytest.mark.parametrize("name", golden_names(["soft_td", "iter_llf"]))
+def test_em_remaining_soft_scripts_golden(S, orc, name):
+    """`Proposed method/Proposed_method_NMSEvsTd.py:44` em and `Proposed method/IterationsvsLLF.py:44` em (soft + LLF)."""
+    meta, g = load_golden(name)
+    n_tx, n_rx, M = int(meta["n_tx"]), int(meta["n_rx"]), int(meta["M"])
+    T_d, T_p, varn, itera = int(meta["T_d"]), int(meta["T_p"]), float(meta["varn"]), int(meta["itera"])
+    Y_d, Y_p, Z_p, PsiTilde_td = _ref_objects(g, n_rx)
+    table = orc.hypothesis_table(orc.qam_constellation(M), n_tx)
+    h0 = g["theta0"].reshape(-1, 1)
+    if "llf_ref" in g:
+        Wd = (g["PsiD"][:, :, None] * g["Xd"][:, None, :]).reshape(T_d, -1)
+        Z_d = [np.kron(Wd[t][None, :], np.eye(n_rx, dtype=np.complex128)) for t in range(T_d)]
+        theta, llf = S.em_iterations_llf(Y_d, Y_p, T_d, T_p, Z_p, Z_d, PsiTilde_td, table, M, varn, itera, h0, n_tx)
+        np.testing.assert_allclose(llf.reshape(-1), g["llf_ref"], rtol=1e-9)
+    else:
+        theta = S.em(Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, table, M, varn, itera, h0)
+    assert relerr(theta.reshape(g["theta_ref"].shape), g["theta_ref"]) < RTOL
+
+
 @pytest.mark.parametrize("name", golden_names("irs"))
 def test_em_irs_elements_golden(S, orc, name):
     """BASELINE.json config 3: `Proposed method/IRS_elements.py:268` em(..., h_initial, N) with its genie stop."""

@@ -97,6 +97,17 @@ def test_irs_elements_script_matches_reference(name):
     assert relerr(th, g["theta_ref"]) < RTOL_THETA
 
 
+@pytest.mark.parametrize("name", golden_names(["soft_td", "iter_llf"]))
+def test_remaining_soft_em_scripts_match_reference(name):
+    """`Proposed method/Proposed_method_NMSEvsTd.py` em and `Proposed method/IterationsvsLLF.py` em (soft EM + LLF)."""
+    meta, g = load_golden(name)
+    th, tr = orc.em(g["Yd"], g["Yp"], g["PsiD"], g["PsiP"], g["Xp"], int(meta["M"]), float(meta["varn"]),
+                    int(meta["itera"]), theta0=g["theta0"], Xd_true=g["Xd"], return_trace=True)
+    assert relerr(th, g["theta_ref"]) < RTOL_THETA
+    if "llf_ref" in g:
+        np.testing.assert_allclose(np.array(tr["llf"]), g["llf_ref"], rtol=1e-11)
+
+
 def test_known_answers_of_baseline_md():
     """BASELINE.md section 3.2 row 3 (seed 1234)."""
     meta, g = load_golden("soft_rev4_s1234")
