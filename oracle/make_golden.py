@@ -327,6 +327,35 @@ def case_pm(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn, partition_r, we
     _save(name, meta, d)
 
 
+def case_pm_ser(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn, partition_r):
+    """`Proposed method/SER/PM_SER.py` em_pm (:55-140): the PM.py estimator started from a RANDOM theta drawn
+    inside the function (:57, needs the globals varh and N), `solve` instead of `lstsq`, no genie stop.  The
+    random start is captured by replaying the RNG state, so that it can be fed to the restatement."""
+    ns = rh.load_functions("Proposed method/SER/PM_SER.py", N=N, n_tx=n_tx, n_rx=n_rx, beta_max=TWO_PI, varh=1)
+    np.random.seed(seed)
+    with rh.quiet():
+        h = ns["channelMatrix"](n_tx, n_rx, N, 1)
+        X_d, aps, qamCons = ns["symbols"](n_tx, M, T_d)
+        ns["qamCons"] = qamCons
+        PsiTilde_tp, PsiTilde_td = ns["irsMatrix"](T_p, T_d, N, 0, 1)
+        PsiTilde_td = np.insert(PsiTilde_td, 0, np.ones((1, T_d), dtype="complex128"), axis=0)
+        X_p = ns["pilotSymbols"](n_tx, M, T_p)
+        Y_p, Y_d, Z_p, Z_d, h_initial = ns["receivedSignals"](T_p, T_d, PsiTilde_tp, PsiTilde_td, n_rx, n_tx, X_d, X_p, h, varn, M)
+        state = np.random.get_state()
+        theta_start = np.random.normal(loc=0, scale=np.sqrt(1 / 2), size=(n_rx * n_tx * (N + 1), 1 * 2)).view(np.complex128)
+        np.random.set_state(state)
+        theta, _xfinal = ns["em_pm"](Y_d, Y_p, T_d, T_p, Z_p, PsiTilde_td, aps, M, varn, itera, h_initial, h, n_tx,
+                                     partition_r, X_d, qamCons)
+    g = dict(h=h, X_d=X_d, X_p=X_p, PsiTilde_tp=PsiTilde_tp, PsiTilde_td=PsiTilde_td, Y_p=Y_p, Y_d=Y_d, Z_p=Z_p,
+             h_initial=theta_start)
+    d = _dense(g, n_tx, n_rx)
+    L = (N + 1) * n_tx
+    meta = dict(kind="pm_ser", order="pm", variant="pm", seed=seed, N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d,
+                itera=itera, varn=varn, partition_r=partition_r, src="Proposed method/SER/PM_SER.py:em_pm")
+    d.update(theta_ref=np.asarray(theta, dtype=np.complex128).reshape(L, n_rx), nmse_ref=_nmse(theta, h))
+    _save(name, meta, d)
+
+
 def case_multi(name, seed, N, n_tx, n_rx, M, T_p, T_d, itera, varn, partition_r,
                script="Proposed method/PMvsMLvsZFvsMMSE.py"):
     """`Proposed method/PMvsMLvsZFvsMMSE.py`: em / em_ml / em_pm with the genie stop
@@ -450,6 +479,8 @@ def main(argv):
         case_parallel("parallel_1x4_s51", 51, 5, 1, 4, 16, 8, 24, 4, 0.1)
     if want("parallel_2x2_s52"):
         case_parallel("parallel_2x2_s52", 52, 4, 2, 2, 4, 30, 20, 3, 0.2)
+    if want("pm_ser_s91"):
+        case_pm_ser("pm_ser_s91", 91, 6, 2, 2, 4, 20, 20, 3, 0.5, 1)
     if want("soft_td_s81"):
         case_soft_td("soft_td_s81", 81, 6, 2, 2, 4, 12, 28, 3, 0.1)
     if want("iter_llf_s82"):

@@ -333,6 +333,19 @@ def test_em_remaining_soft_scripts_golden(S, orc, name):
     assert relerr(theta.reshape(g["theta_ref"].shape), g["theta_ref"]) < RTOL
 
 
+@pytest.mark.parametrize("name", golden_names("pm_ser"))
+def test_em_pm_ser_golden(S, orc, name):
+    """`Proposed method/SER/PM_SER.py:55` em_pm: the PM estimator from a random start, all iterations executed."""
+    meta, g = load_golden(name)
+    n_tx, n_rx, M = int(meta["n_tx"]), int(meta["n_rx"]), int(meta["M"])
+    Y_d, Y_p, Z_p, PsiTilde_td = _ref_objects(g, n_rx)
+    cons = orc.qam_constellation(M)
+    th = S.em_pm(Y_d, Y_p, int(meta["T_d"]), int(meta["T_p"]), Z_p, PsiTilde_td, orc.hypothesis_table(cons, n_tx), M,
+                 float(meta["varn"]), int(meta["itera"]), g["theta0"].reshape(-1, 1), g["h"].reshape(-1), n_tx,
+                 int(meta["partition_r"]), None, cons, genie_stop=False)
+    assert relerr(th.reshape(g["theta_ref"].shape), g["theta_ref"]) < RTOL
+
+
 @pytest.mark.parametrize("name", golden_names("irs"))
 def test_em_irs_elements_golden(S, orc, name):
     """BASELINE.json config 3: `Proposed method/IRS_elements.py:268` em(..., h_initial, N) with its genie stop."""

@@ -108,6 +108,16 @@ def test_remaining_soft_em_scripts_match_reference(name):
         np.testing.assert_allclose(np.array(tr["llf"]), g["llf_ref"], rtol=1e-11)
 
 
+@pytest.mark.parametrize("name", golden_names("pm_ser"))
+def test_pm_ser_script_matches_reference(name):
+    """`Proposed method/SER/PM_SER.py` em_pm: random start (captured in the fixture), `solve`, no genie stop."""
+    meta, g = load_golden(name)
+    th = orc.em_pm(g["Yd"], g["Yp"], g["PsiD"], g["PsiP"], g["Xp"], int(meta["M"]), float(meta["varn"]),
+                   int(meta["itera"]), g["theta0"], h_true=g["h"], partition_r=int(meta["partition_r"]),
+                   weighted=False, genie_stop=False, how="solve")
+    assert relerr(th, g["theta_ref"]) < 1e-9
+
+
 def test_known_answers_of_baseline_md():
     """BASELINE.md section 3.2 row 3 (seed 1234)."""
     meta, g = load_golden("soft_rev4_s1234")
