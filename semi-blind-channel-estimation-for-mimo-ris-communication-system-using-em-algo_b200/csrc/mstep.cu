@@ -1522,24 +1522,17 @@ cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, c
         thg = th_scratch;
         smem = sizeof(cplx) * (3 * CH_NB * CH_DS);
     }
-    // CTA shape (SBCE_CHOL_VARIANT selects alternatives for experiments)
+    // SBCE_CHOL_VARIANT=1 selects the predecessor kernel (two barriers per panel, shared-memory diagonal factor)
+    // for A/B runs.  CTA shapes measured on B200 (N=64, 4x4: L=260, 592 trials) for the look-ahead kernel:
+    // 128 threads x 4 CTAs/SM 0.98 ms, 96 x 5 1.27 ms, 256 x 2 1.57 ms, 160 x 3 1.45 ms, 128 x 5 (96 registers)
+    // 1.11 ms -- latency bound, more resident trials per SM win even though their factors no longer fit in L2.
     static int variant = -1;
     if (variant < 0) {
         const char* v = getenv("SBCE_CHOL_VARIANT");
         variant = v ? atoi(v) : 0;
     }
-    // measured on B200 (N=64, 4x4: L=260, 592 trials): 128x4 1.40 ms, 256x2 2.0 ms, 288x1 2.9 ms -- the kernel
-    // is latency bound, more resident trials per SM win even though their factors no longer all fit in L2
-    switch (variant) {
-        case 0: return run_chol2<128, 4>(d, nb, G, theta, active, stat, smem, thg, s);
-        case 6: return run_chol2<256, 2>(d, nb, G, theta, active, stat, smem, thg, s);
-        case 7: return run_chol2<96, 5>(d, nb, G, theta, active, stat, smem, thg, s);
-        case 2: return run_chol<256, 2>(d, nb, G, theta, active, stat, smem, thg, s);
-        case 3: return run_chol<288, 1>(d, nb, G, theta, active, stat, smem, thg, s);
-        case 4: return run_chol<64, 8>(d, nb, G, theta, active, stat, smem, thg, s);
-        case 5: return run_chol<96, 5>(d, nb, G, theta, active, stat, smem, thg, s);
-        default: return run_chol<128, 4>(d, nb, G, theta, active, stat, smem, thg, s);
-    }
+    if (variant == 1) return run_chol<128, 4>(d, nb, G, theta, active, stat, smem, thg, s);
+    return run_chol2<128, 4>(d, nb, G, theta, active, stat, smem, thg, s);
 }
 
 }  // namespace sbce
