@@ -189,3 +189,51 @@ def test_structured_product_helpers():
         for j in range(n_tx):
             for r in range(n_rx):
                 assert np.isclose(Z[r, sbce.signal_model.design_index(npr, j, r, n_tx, n_rx)], psi[npr] * x[j], rtol=1e-15, atol=0)
+
+
+def test_problem_flags_and_shapes_for_the_layout_variants():
+    L = sbce._lib
+    p = sbce.Problem(N=6, n_tx=2, n_rx=3, M=16, T_p=0, T_d=12, itera=2, superimposed=True, zero_start=True)
+    c = p.cfg(5)
+    assert c.flags & L.FLAG_SUPERIMPOSED and c.flags & L.FLAG_ZERO_START and not c.flags & L.FLAG_PSI_SHARED
+    assert p.shapes(5)["Xp"] == (5, 12, 2) and p.shapes(5)["Yp"] == (5, 0, 3)          # offsets ride in Xp
+    p = sbce.Problem(N=6, n_tx=2, n_rx=3, M=16, T_p=8, T_d=12, itera=2, psip_shared=True)
+    sh = p.shapes(5)
+    assert sh["PsiP"] == (8, 7) and sh["PsiD"] == (5, 12, 7) and p.cfg(5).flags & L.FLAG_PSIP_SHARED
+    p = sbce.Problem(N=6, n_tx=2, n_rx=3, M=16, T_p=8, T_d=12, itera=2, psi_shared=True)
+    assert p.shapes(5)["PsiP"] == (8, 7) and p.shapes(5)["PsiD"] == (12, 7)
+    p = sbce.Problem(N=6, n_tx=2, n_rx=3, M=16, T_p=8, T_d=12, itera=2, mode="zf", zf_stop_guard=True, genie_stop=True)
+    assert p.cfg(1).flags & L.FLAG_ZF_STOP_GUARD and p.cfg(1).flags & L.FLAG_GENIE_STOP and p.cfg(1).mode == L.MODE_ZF
+    # superimposed pilots need T_p = 0 and a tree mode: rejected by the library's argument check (no GPU needed)
+    for bad in (sbce.Problem(N=6, n_tx=2, n_rx=3, M=16, T_p=4, T_d=12, itera=2, superimposed=True),
+                sbce.Problem(N=6, n_tx=2, n_rx=3, M=16, T_p=0, T_d=12, itera=2, superimposed=True, mode="pm_beta")):
+        with pytest.raises(sbce.SbceError):
+            sbce.engine.workspace_bytes(bad, 1)
+
+
+def test_pilot_design_rows_are_recovered_from_the_dense_Z_p():
+    """The reference hands the estimator dense Kronecker matrices Z_p[t] = psi_t^T (x) x_t^T (x) I; the adapter reads
+    w_t = psi_t (x) x_t from row 0 and splits it back into (psi, x) -- exact up to a common scalar."""
+    from importlib import import_module
+
+    est = import_module(sbce.__name__ + ".estimators")
+    rng = np.random.default_rng(3)
+    n_tx, n_rx, N1, T_p = 3, 2, 5, 7
+    psi = np.exp(2j * np.pi * rng.random((T_p, N1)))
+    psi[:, -1] = 0.0                                         # a switched-off element (quirk Q3)
+    x = sbce.qam.constellation(16)[rng.integers(0, 16, (T_p, n_tx))]
+    Z_p = [np.kron(np.kron(psi[t][None, :], x[t][None, :]), np.eye(n_rx)) for t in range(T_p)]
+    PsiP, Xp = est._pilot_factors(Z_p, n_rx, n_tx, N1)
+    W = (PsiP[:, :, None] * Xp[:, None, :]).reshape(T_p, -1)
+    W_ref = (psi[:, :, None] * x[:, None, :]).reshape(T_p, -1)
+    assert np.abs(W - W_ref).max() < 1e-13
+
+
+def test_em_parallel_validates_shapes_before_touching_the_device():
+    cons = sbce.qam.constellation(4)
+    table = np.array([[c] for c in cons])
+    Y = [np.zeros((2, 1), complex) for _ in range(5)]
+    with pytest.raises(ValueError):
+        sbce.em_parallel(Y, 6, None, [], [], 0, 5, 1, np.ones((4, 5), complex), table, 4, 0.1, 2, 3)   # T mismatch
+    with pytest.raises(ValueError):
+        sbce.em_parallel(Y, 5, None, [], [], 0, 5, 1, np.ones((3, 5), complex), table, 4, 0.1, 2, 3)   # N+1 rows expected
