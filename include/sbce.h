@@ -26,9 +26,16 @@
  *   - hypothesis index k = sum_j idx_j * M^(n_tx-1-j) (itertools.product order,
  *     Proposed method/PM.py:25-31), constellation index = iQ*sqrt(M)+iI
  *     (Proposed method/QAM.py:320-322).
- *   - all calls are asynchronous on `stream` unless the name ends in _host;
- *     the library keeps no global mutable state except a per-process scratch
- *     cache used by the *_host convenience entry points.
+ *   - all calls are asynchronous on `stream` unless the name ends in _host.
+ *     Process-wide state is limited to: the per-device scratch cache and streams
+ *     of the *_host entry points (one mutex per device, so host threads driving
+ *     different GPUs run concurrently), the launch counter (atomic) and the
+ *     optional phase profiler (atomic switch, mutex-protected span list).  The
+ *     *_host entry points restore the caller's current device and drain their
+ *     streams on every return path, errors included.
+ *   - limits: n_tx, n_rx <= 8; M in {4, 16, 64}; N + 1 + n_tx^2 <= 908 (the
+ *     normal-equation kernels stage phase rows in shared memory); trials are
+ *     processed in chunks of at most 65535 per launch whatever the workspace.
  *   - return value: 0 ok, <0 argument error (SBCE_E_*), >0 a cudaError_t.
  *     Per-trial numerical status is reported in status[b] (bit mask).
  */
@@ -115,11 +122,13 @@ typedef struct sbce_io {
     const double* Xd_true; /* [B][T_d][n_tx] nullable: needed for llf[] (as-coded LLF)         */
     double* theta;         /* [B][L][n_rx]   out                                               */
     int32_t* kstar;        /* [B][T_d] int32 out, nullable: decisions of the last executed
-                              iteration, made before its M-step (SER/log_max_SER.py:77-78)     */
+                              iteration, made before its M-step (SER/log_max_SER.py:77-78);
+                              -1 in the PM / PM_BETA modes, which take no joint decision        */
     double* llf;           /* [B][itera] float64 out, nullable: LLF exactly as coded
                               (ML_detecctor.py:84); entries of skipped iterations are NaN      */
     double* lse;           /* [B][itera] float64 out, nullable: sum_t log sum_k exp(-d2/varn^2)
-                              at the theta that entered the iteration                          */
+                              at the theta that entered the iteration (SOFT / HARD modes; NaN
+                              in the PM, ZF and MMSE modes, which never form the sum)           */
     double* nmse;          /* [B] float64 out, nullable (needs h_true)                         */
     int32_t* iters;        /* [B] int32 out, nullable: iterations executed                     */
     int32_t* status;       /* [B] int32 out, nullable: SBCE_ST_* bit mask                      */
@@ -144,6 +153,10 @@ int sbce_em_batch(const sbce_cfg* cfg, const sbce_io* io, void* workspace, size_
  * host->device, runs sbce_em_batch on an internal stream, copies the outputs
  * back and synchronises.  `device` selects the GPU. */
 int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device);
+
+/* Batch size from which sbce_em_batch_host() pipelines a call in two halves (the upload of the
+ * second half overlaps the kernels of the first). */
+int sbce_host_split_threshold(void);
 
 /* Stand-alone E-step sweep (posterior statistics at a given theta), device
  * pointers.  stat_m [B][T_d][n_tx], stat_R [B][T_d][n_tx][n_tx] complex128,

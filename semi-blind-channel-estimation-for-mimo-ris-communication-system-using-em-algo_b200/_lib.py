@@ -50,7 +50,7 @@ PHASES_KIND = {"random": 0, "dft": 1}
 EXPORTS = ["sbce_version", "sbce_error_string", "sbce_device_count", "sbce_workspace_bytes", "sbce_em_batch",
            "sbce_em_batch_host", "sbce_estep", "sbce_mstep", "sbce_accumulate_nmse", "sbce_measure_fp64_peak",
            "sbce_launch_count", "sbce_profile_begin", "sbce_profile_end", "sbce_generate_batch", "sbce_ls_start",
-           "sbce_accumulate_ser"]
+           "sbce_accumulate_ser", "sbce_host_split_threshold"]
 
 PHASES = ["setup", "heff_qr", "enum", "gram", "rhs", "chol", "metrics"]
 
@@ -84,6 +84,7 @@ def load():
     lib.sbce_accumulate_ser.argtypes = [C.POINTER(Cfg), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.sbce_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.sbce_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
+    lib.sbce_host_split_threshold.restype = C.c_int
     lib.sbce_launch_count.restype = C.c_int64
     lib.sbce_launch_count.argtypes = [C.c_int32]
     _lib = lib

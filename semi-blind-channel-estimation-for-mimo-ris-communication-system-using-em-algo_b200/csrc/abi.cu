@@ -16,14 +16,19 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // ---- optional per-phase CUDA-event timing (bench.py's roofline numbers) --------------------------
 // Events are recorded on the launch stream around every phase while profiling is on; the cost is one
 // cudaEventRecord pair per phase launch.  sbce_profile_end() synchronises and sums the intervals.
+// The switch is an atomic; the span list and the event pool are only touched under g_prof_mu, so concurrent
+// callers (one host thread per GPU) may run with profiling armed.
 struct PhaseSpan { int phase; cudaEvent_t a, b; };
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
 static std::vector<PhaseSpan> g_spans;
 static std::vector<cudaEvent_t> g_event_pool;
 static std::mutex g_prof_mu;
 
 static cudaEvent_t prof_event() {
-    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    {
+        std::lock_guard<std::mutex> lock(g_prof_mu);
+        if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    }
     cudaEvent_t e;
     cudaEventCreate(&e);
     return e;
@@ -31,11 +36,16 @@ static cudaEvent_t prof_event() {
 
 struct PhaseScope {
     bool on; int phase; cudaStream_t s; cudaEvent_t a;
-    PhaseScope(int ph, cudaStream_t st) : on(g_prof_on), phase(ph), s(st), a(nullptr) {
+    PhaseScope(int ph, cudaStream_t st) : on(g_prof_on.load(std::memory_order_relaxed)), phase(ph), s(st), a(nullptr) {
         if (on) { a = prof_event(); cudaEventRecord(a, s); }
     }
     ~PhaseScope() {
-        if (on) { cudaEvent_t b = prof_event(); cudaEventRecord(b, s); g_spans.push_back({phase, a, b}); }
+        if (on) {
+            cudaEvent_t b = prof_event();
+            cudaEventRecord(b, s);
+            std::lock_guard<std::mutex> lock(g_prof_mu);
+            g_spans.push_back({phase, a, b});
+        }
     }
 };
 
@@ -46,6 +56,8 @@ static int make_dims(const sbce_cfg* c, Dims* d, bool with_estep = true) {
     int sq = 0;
     if (c->M == 4) sq = 2; else if (c->M == 16) sq = 4; else if (c->M == 64) sq = 8; else return SBCE_E_UNSUPPORTED;
     if (c->n_tx > 8 || c->n_rx > 8) return SBCE_E_UNSUPPORTED;
+    // the normal-equation kernels stage chunks of the phase rows in shared memory (mstep.cu: gram_supports)
+    if (!gram_supports(c->N + 1, c->n_tx)) return SBCE_E_UNSUPPORTED;
     if (c->n_tx <= 4 && !(c->n_rx <= 4 || c->n_rx == 6 || c->n_rx == 8)) return SBCE_E_UNSUPPORTED;
     if (c->mode < SBCE_MODE_SOFT || c->mode > SBCE_MODE_MMSE) return SBCE_E_UNSUPPORTED;
     if (with_estep) {
@@ -139,6 +151,12 @@ static int estep_dispatch(const Dims& d, int nb, const double* Yd, const double*
 static inline Dims pilot_dims(const Dims& d) { Dims dp = d; dp.psi_shared = d.psiP_shared; return dp; }
 
 static int em_chunk(const Dims& d, int nb, const sbce_io& io, Workspace& ws, cudaStream_t s) {
+    // Only the exhaustive modes produce a per-symbol log-sum (lse) and, with the detector modes, joint decisions
+    // (kstar).  The partitioned modes write neither: kstar reads -1 and lse stays NaN instead of leaking whatever
+    // the buffers held.
+    const bool tree = d.mode == SBCE_MODE_SOFT || d.mode == SBCE_MODE_HARD;
+    const bool decides = tree || d.mode == SBCE_MODE_ZF || d.mode == SBCE_MODE_MMSE;
+    if (io.kstar && !decides) CK(cudaMemsetAsync(io.kstar, 0xFF, (size_t)nb * d.T_d * sizeof(int32_t), s));
     {
         PhaseScope ps(SBCE_PHASE_SETUP, s);
         CK(launch_init_state(d, nb, io.theta0, io.theta, ws.active, ws.stat, io.iters, io.llf, io.lse, s));
@@ -163,7 +181,8 @@ static int em_chunk(const Dims& d, int nb, const sbce_io& io, Workspace& ws, cud
         {
             PhaseScope ps(SBCE_PHASE_METRICS, s);
             CK(launch_after_iteration(d, nb, l, io.theta, io.h_true, io.Yp, io.Yd, io.PsiP, io.PsiD, io.Xp,
-                                      io.Xd_true, io.varn, ws.lse_sym, ws.active, io.iters, io.llf, io.lse, s));
+                                      io.Xd_true, io.varn, tree ? ws.lse_sym : nullptr, ws.active, io.iters, io.llf,
+                                      io.lse, s));
         }
     }
     {
@@ -220,7 +239,7 @@ const char* sbce_error_string(int code) {
         case 0: return "ok";
         case SBCE_E_NULL: return "required pointer is null";
         case SBCE_E_SHAPE: return "invalid shape parameter";
-        case SBCE_E_UNSUPPORTED: return "unsupported configuration (n_tx,n_rx<=8; n_tx<=4: n_rx in {1,2,3,4,6,8}; M in {4,16,64}; exhaustive modes with n_tx>4 need n_tx*log2(M)<=24)";
+        case SBCE_E_UNSUPPORTED: return "unsupported configuration (n_tx,n_rx<=8; n_tx<=4: n_rx in {1,2,3,4,6,8}; M in {4,16,64}; N+1+n_tx^2<=908; exhaustive modes with n_tx>4 need n_tx*log2(M)<=24)";
         case SBCE_E_WORKSPACE: return "workspace too small for one trial";
         case SBCE_E_NODEVICE: return "no CUDA device";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
@@ -244,8 +263,12 @@ int sbce_workspace_bytes(const sbce_cfg* cfg, int32_t trials_in_flight, size_t* 
     return 0;
 }
 
+// Trials per chunk: as many as the workspace holds, at most `want`, and at most 65535 -- the chunk size is
+// gridDim.y of the Gram / E-step / generator launches.
+constexpr int SBCE_MAX_CHUNK = 65535;
 static int trials_fitting(const Dims& d, size_t bytes, int want) {
     Workspace ws;
+    if (want > SBCE_MAX_CHUNK) want = SBCE_MAX_CHUNK;
     if (carve_workspace(d, 1, nullptr, &ws) > bytes) return 0;
     int lo = 1, hi = want;
     while (lo < hi) {
@@ -345,8 +368,15 @@ int sbce_generate_batch(const sbce_cfg* cfg, const sbce_gen* gen, const sbce_io*
     if (gen->pilot_design < SBCE_PILOTS_PM || gen->pilot_design > SBCE_PILOTS_TOP) return SBCE_E_UNSUPPORTED;
     if (gen->data_phases < SBCE_PHASES_RANDOM || gen->data_phases > SBCE_PHASES_DFT) return SBCE_E_UNSUPPORTED;
     if (cfg->batch == 0) return 0;
-    CK(launch_generate(d, cfg->batch, gen, *io, (double*)io->h_true, (double*)io->Xp, (double*)io->Xd_true,
-                       (double*)io->PsiP, (double*)io->PsiD, (double*)io->Yp, (double*)io->Yd, (cudaStream_t)stream));
+    // the trial index is gridDim.y of the generator kernels: at most 65535 trials per launch
+    for (int b0 = 0; b0 < cfg->batch; b0 += SBCE_MAX_CHUNK) {
+        const int nb = (cfg->batch - b0 < SBCE_MAX_CHUNK) ? cfg->batch - b0 : SBCE_MAX_CHUNK;
+        sbce_gen g = *gen;
+        g.trial0 = gen->trial0 + b0;
+        const sbce_io o = offset_io(d, *io, (size_t)b0);
+        CK(launch_generate(d, nb, &g, o, (double*)o.h_true, (double*)o.Xp, (double*)o.Xd_true, (double*)o.PsiP,
+                           (double*)o.PsiD, (double*)o.Yp, (double*)o.Yd, (cudaStream_t)stream));
+    }
     return 0;
 }
 
@@ -391,13 +421,13 @@ int sbce_profile_begin(void) {
     std::lock_guard<std::mutex> lock(g_prof_mu);
     for (auto& sp : g_spans) { g_event_pool.push_back(sp.a); g_event_pool.push_back(sp.b); }
     g_spans.clear();
-    g_prof_on = true;
+    g_prof_on.store(true);
     return 0;
 }
 
 int sbce_profile_end(double* ms_per_phase, int64_t* spans_per_phase, int32_t n_phases) {
     std::lock_guard<std::mutex> lock(g_prof_mu);
-    g_prof_on = false;
+    g_prof_on.store(false);
     if (!ms_per_phase || n_phases < 1) return SBCE_E_NULL;
     for (int i = 0; i < n_phases; ++i) { ms_per_phase[i] = 0.0; if (spans_per_phase) spans_per_phase[i] = 0; }
     for (auto& sp : g_spans) {
@@ -431,9 +461,10 @@ struct DevPool {
     cudaStream_t stream = nullptr;   // compute + device->host
     cudaStream_t copy = nullptr;     // host->device, runs ahead of the compute stream
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::mutex mu;                   // one caller at a time per device; different devices run concurrently
 };
-std::mutex g_mu;
-DevPool g_pool[16];
+constexpr int SBCE_MAX_DEVICES = 64;
+DevPool g_pool[SBCE_MAX_DEVICES];
 
 int pool_get(int dev, size_t bytes, DevPool** out) {
     DevPool& P = g_pool[dev];
@@ -453,7 +484,41 @@ int pool_get(int dev, size_t bytes, DevPool** out) {
     *out = &P;
     return 0;
 }
+
+// Restores the calling thread's current device on scope exit (the host route selects `device` itself).
+struct DeviceGuard {
+    int prev = -1;
+    bool armed = false;
+    int enter(int dev) {
+        CK(cudaGetDevice(&prev));
+        armed = true;
+        if (prev != dev) CK(cudaSetDevice(dev));
+        return 0;
+    }
+    ~DeviceGuard() {
+        if (armed) { int cur = -1; if (cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev); }
+    }
+};
+
+// Drains both streams of the pool on scope exit: whatever path leaves sbce_em_batch_host (error returns
+// included), no DMA is still reading or writing the caller's host buffers afterwards.
+struct DrainGuard {
+    DevPool* P = nullptr;
+    ~DrainGuard() {
+        if (P) {
+            if (P->copy) cudaStreamSynchronize(P->copy);
+            if (P->stream) cudaStreamSynchronize(P->stream);
+        }
+    }
+};
+
+// Batch size from which the host route splits a call in two halves (upload of the second half overlaps the
+// kernels of the first); below it the kernels lose more from the smaller launch than the overlap wins
+// (measured on B200 at the north-star size).  sbce_host_split_threshold() exposes it to tests.
+constexpr int SBCE_HOST_SPLIT_MIN_BATCH = 1184;
 }  // namespace
+
+int sbce_host_split_threshold(void) { return SBCE_HOST_SPLIT_MIN_BATCH; }
 
 int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device) {
     Dims d;
@@ -462,9 +527,11 @@ int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device) {
     rc = check_io(d, io);
     if (rc) return rc;
     if (cfg->batch == 0) return 0;
-    if (device < 0 || device >= 16 || device >= sbce_device_count()) return SBCE_E_NODEVICE;
-    std::lock_guard<std::mutex> lock(g_mu);
-    CK(cudaSetDevice(device));
+    if (device < 0 || device >= SBCE_MAX_DEVICES || device >= sbce_device_count()) return SBCE_E_NODEVICE;
+    std::lock_guard<std::mutex> lock(g_pool[device].mu);
+    DeviceGuard dg;
+    rc = dg.enter(device);
+    if (rc) return rc;
     const size_t B = (size_t)cfg->batch;
     const size_t Ln = (size_t)d.L * d.n_rx * 16;
     const size_t psiB = d.psi_shared ? 1 : B, psiPB = d.psiP_shared ? 1 : B;
@@ -505,6 +572,8 @@ int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device) {
     DevPool* P = nullptr;
     rc = pool_get(device, io_bytes + ws_bytes + 256, &P);
     if (rc) return rc;
+    DrainGuard drain;
+    drain.P = P;
     char* base = (char*)P->p;
     cudaStream_t s = P->stream;
     sbce_io dio;
@@ -516,9 +585,8 @@ int sbce_em_batch_host(const sbce_cfg* cfg, const sbce_io* io, int32_t device) {
     dio.iters = (int32_t*)dp(oIt); dio.status = (int32_t*)dp(oSt);
 
     // Large batches go in two halves: the host->device copy of the second half overlaps the kernels of
-    // the first (copy stream runs ahead; the compute stream waits on one event per half).  Below ~1200
-    // trials the kernels lose more from the smaller launch than the overlap wins (measured on B200).
-    const int nhalf = (cfg->batch >= 1184) ? 2 : 1;
+    // the first (copy stream runs ahead; the compute stream waits on one event per half).
+    const int nhalf = (cfg->batch >= SBCE_HOST_SPLIT_MIN_BATCH) ? 2 : 1;
     const int half = (cfg->batch + nhalf - 1) / nhalf;
     struct Part { Seg* q; size_t per_trial; };
     Part ins[] = {{&sYd, (size_t)d.T_d * d.n_rx * 16}, {&sYp, (size_t)d.T_p * d.n_rx * 16},

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/sbce.h"
 
 namespace sbce {
@@ -109,6 +111,7 @@ cudaError_t launch_enum(const Dims& d, int nb, const double* qr, const double* v
 cudaError_t launch_normal_equations(const Dims& d, int nb, const double* Psi, int T, const double* Y,
                                     const double* sm, const double* sR, const double* Ginit, double* Gout,
                                     const int32_t* active, cudaStream_t s);
+bool gram_supports(int N1, int n_tx);   // phase rows short enough for the shared-memory staging of the Gram kernels
 cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
                               double* th_scratch, cudaStream_t s);
 // metrics (metrics.cu)
@@ -132,5 +135,21 @@ cudaError_t launch_accumulate_ser(const Dims& d, int nb, const int32_t* kstar, c
                                   cudaStream_t s);
 
 void count_launch(int n = 1);
+
+// Opt-in to more than 48 KB of dynamic shared memory, once per (kernel instantiation, device) instead of on
+// every launch of the EM loop.  Each launcher keeps one `static SmemOptIn` per kernel it launches.
+struct SmemOptIn {
+    std::atomic<size_t> have[64];
+};
+inline cudaError_t opt_in_smem(SmemOptIn& st, const void* kernel, size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && st.have[dev].load(std::memory_order_relaxed) >= smem) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) st.have[dev].store(smem, std::memory_order_relaxed);
+    return e;
+}
 
 }  // namespace sbce

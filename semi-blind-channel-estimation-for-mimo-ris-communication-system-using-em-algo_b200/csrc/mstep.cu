@@ -14,15 +14,14 @@
 //    RIS indices owns the whole n_tx x n_tx block  sum_t conj(psi[t,n]) psi[t,n'] R_t ; because R_t is
 //    Hermitian its 2 n_tx^2 real accumulators are [p_r ; p_i] (2 x T) times a real (T x n_tx^2) matrix
 //    built from diag(R_t) and the upper entries, i.e. the whole Gram is ONE real GEMM that runs on the
-//    FP64 tensor path (k_gram_mma4 for n_tx = 4, k_gram_mma<NTX> for n_tx = 5..8; scalar k_gram<NTX>
-//    below 4).  Only the lower triangle is produced.  The last CTA of each trial writes B^H as extra
+//    FP64 tensor path (k_gram_tma4 for n_tx = 4, k_gram_mma<NTX> for n_tx = 5..8 and long rows; scalar
+//    k_gram<NTX> below 4).  Only the lower triangle is produced.  The last CTA of each trial writes B^H as extra
 //    rows below the matrix, and the padding.
 //  * k_chol: one CTA per trial, LEFT-looking blocked complex Cholesky (panel width 16) on the augmented
 //    lower trapezoid [G ; B^H], panel updates and the triangular solve as DMMA products; the B^H rows
 //    come out as (C^-1 B)^H for free, so only the back substitution C^H theta = z remains.  A
 //    non-positive pivot flags the trial (status bit) instead of poisoning the batch.
 #include <math.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -32,7 +31,7 @@ namespace sbce {
 // Gram + right-hand side
 // ---------------------------------------------------------------------------
 constexpr int GR_THREADS = 256;
-constexpr int GR_TC = 16;  // symbols per shared-memory chunk
+constexpr int GR_TC = 16;  // symbols per shared-memory chunk (default; shrunk at launch for very long psi rows)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -147,7 +146,7 @@ __device__ __forceinline__ void gram_rhs_cta(const Dims& d, int T, int b, cplx* 
 // one thread per column l with n_rx accumulators, plus the identity padding of the trapezoid.
 // Both kinds of CTA stage the same psi chunks in shared memory.
 template <int NTX>
-__global__ void __launch_bounds__(GR_THREADS, 2) k_gram(Dims d, int T, const cplx* __restrict__ Psi,
+__global__ void __launch_bounds__(GR_THREADS, 2) k_gram(Dims d, int T, int TC, const cplx* __restrict__ Psi,
                                                      const cplx* __restrict__ sR, const cplx* __restrict__ Y,
                                                      const cplx* __restrict__ sm, const cplx* __restrict__ Ginit,
                                                      cplx* __restrict__ Gout, const int32_t* __restrict__ active) {
@@ -156,8 +155,8 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_gram(Dims d, int T, const cpl
     if (active != nullptr && active[b] == 0) return;
     const int N1 = d.N1;
     const int P = N1 * (N1 + 1) / 2;
-    cplx* sPsi = gsm;               // [GR_TC][N1]
-    cplx* sRr = sPsi + GR_TC * N1;  // [GR_TC][NTX*NTX]  (rhs CTA: [GR_TC][NTX][n_rx] conj(m_i y_r))
+    cplx* sPsi = gsm;            // [TC][N1]
+    cplx* sRr = sPsi + TC * N1;  // [TC][NTX*NTX]  (rhs CTA: sized from the dynamic shared memory it finds)
     const cplx* psi_b = Psi + (size_t)(d.psi_shared ? 0 : b) * T * N1;
     const size_t gstride = (size_t)d.Ltot * d.Lp;
     cplx* Gb = Gout + (size_t)b * gstride;
@@ -193,27 +192,27 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_gram(Dims d, int T, const cpl
 
     const cplx* R_b = sR + (size_t)b * T * NTX * NTX;
     // two-stage cp.async pipeline: chunk c+1 streams into the other buffer while chunk c is consumed
-    const int stage_elems = GR_TC * (N1 + NTX * NTX);      // complex elements per stage
+    const int stage_elems = TC * (N1 + NTX * NTX);      // complex elements per stage
     auto issue = [&](int chunk, int buf) {
-        const int t0 = chunk * GR_TC;
-        const int tc = min(GR_TC, T - t0);
+        const int t0 = chunk * TC;
+        const int tc = min(TC, T - t0);
         cplx* dpsi = gsm + buf * stage_elems;
-        cplx* dR = dpsi + GR_TC * N1;
+        cplx* dR = dpsi + TC * N1;
         const cplx* spsi = psi_b + (size_t)t0 * N1;
         const cplx* sRg = R_b + (size_t)t0 * NTX * NTX;
         for (int e = threadIdx.x; e < tc * N1; e += GR_THREADS) cp_async16(dpsi + e, spsi + e);
         for (int e = threadIdx.x; e < tc * NTX * NTX; e += GR_THREADS) cp_async16(dR + e, sRg + e);
         cp_async_commit();
     };
-    const int nchunk = (T + GR_TC - 1) / GR_TC;
+    const int nchunk = (T + TC - 1) / TC;
     if (nchunk > 0) issue(0, 0);
     for (int ck = 0; ck < nchunk; ++ck) {
         const int buf = ck & 1;
         if (ck + 1 < nchunk) { issue(ck + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncthreads();
-        const int tc = min(GR_TC, T - ck * GR_TC);
+        const int tc = min(TC, T - ck * TC);
         const cplx* cPsi = gsm + buf * stage_elems;
-        const cplx* cR = cPsi + GR_TC * N1;
+        const cplx* cR = cPsi + TC * N1;
         if (is_pair) {
 #pragma unroll 4
             for (int tt = 0; tt < tc; ++tt) {
@@ -278,133 +277,10 @@ __device__ __forceinline__ int gram_bcol_offset(int col) {
     return 2 * up[q] + ((col - 4) & 1);
 }
 
-constexpr int GM_TC = 32;  // symbols per stage of the tensor-path Gram
-__global__ void __launch_bounds__(GR_THREADS, 2) k_gram_mma4(Dims d, int T, const cplx* __restrict__ Psi,
-                                                           const cplx* __restrict__ sR, const cplx* __restrict__ Y,
-                                                           const cplx* __restrict__ sm, const cplx* __restrict__ Ginit,
-                                                           cplx* __restrict__ Gout, const int32_t* __restrict__ active) {
-    constexpr int NTX = 4;
-    extern __shared__ double2 gsm[];
-    const int b = blockIdx.y;
-    if (active != nullptr && active[b] == 0) return;
-    const int N1 = d.N1;
-    const int P = N1 * (N1 + 1) / 2;
-    const cplx* psi_b = Psi + (size_t)(d.psi_shared ? 0 : b) * T * N1;
-    const size_t gstride = (size_t)d.Ltot * d.Lp;
-    cplx* Gb = Gout + (size_t)b * gstride;
-    const cplx* Gi = Ginit ? Ginit + (size_t)b * gstride : nullptr;
-    if (blockIdx.x == gridDim.x - 1) {
-        gram_rhs_cta<NTX>(d, T, b, gsm, gsm + GR_TC * N1, psi_b, Y, sm, Gi, Gb);
-        return;
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
-    // pairs of this lane: tile u (0,1), row half h (0,1) -> item
-    int pn[2][2], pnp[2][2];
-    bool pv[2][2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int item = blockIdx.x * GR_THREADS + (2 * warp + u) * 16 + g + 8 * h;
-            pv[u][h] = item < P;
-            item = min(item, P - 1);
-            int n = (int)((sqrt(8.0 * item + 1.0) - 1.0) * 0.5);
-            while ((n + 1) * (n + 2) / 2 <= item) ++n;
-            while (n * (n + 1) / 2 > item) --n;
-            pn[u][h] = n;
-            pnp[u][h] = item - n * (n + 1) / 2;
-        }
-    const int boff0 = gram_bcol_offset(g), boff1 = gram_bcol_offset(8 + g);
-    double accr[2][2][4], acci[2][2][4];  // [tile][n-tile][c0..c3]
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { accr[u][nt][e] = 0.0; acci[u][nt][e] = 0.0; }
-
-    const cplx* R_b = sR + (size_t)b * T * NTX * NTX;
-    const int stage_elems = GM_TC * (N1 + NTX * NTX);
-    auto issue = [&](int chunk, int buf) {
-        const int t0 = chunk * GM_TC;
-        const int tc = min(GM_TC, T - t0);
-        cplx* dpsi = gsm + buf * stage_elems;
-        cplx* dR = dpsi + GM_TC * N1;
-        const cplx* spsi = psi_b + (size_t)t0 * N1;
-        const cplx* sRg = R_b + (size_t)t0 * NTX * NTX;
-        for (int e = threadIdx.x; e < tc * N1; e += GR_THREADS) cp_async16(dpsi + e, spsi + e);
-        for (int e = threadIdx.x; e < tc * NTX * NTX; e += GR_THREADS) cp_async16(dR + e, sRg + e);
-        if (tc < GM_TC) {  // ragged last chunk: symbols beyond T contribute zero
-            for (int e = tc * N1 + threadIdx.x; e < GM_TC * N1; e += GR_THREADS) dpsi[e] = mk(0.0, 0.0);
-            for (int e = tc * NTX * NTX + threadIdx.x; e < GM_TC * NTX * NTX; e += GR_THREADS) dR[e] = mk(0.0, 0.0);
-        }
-        cp_async_commit();
-    };
-    const int nchunk = (T + GM_TC - 1) / GM_TC;
-    if (nchunk > 0) issue(0, 0);
-    for (int ck = 0; ck < nchunk; ++ck) {
-        const int buf = ck & 1;
-        if (ck + 1 < nchunk) { issue(ck + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-        __syncthreads();
-        const cplx* cPsi = gsm + buf * stage_elems;
-        const double* cR = (const double*)(cPsi + GM_TC * N1);
-#pragma unroll
-        for (int ks = 0; ks < GM_TC / 8; ++ks) {
-            const int tlo = ks * 8 + tig, thi = tlo + 4;
-            const double b00 = cR[tlo * 32 + boff0], b01 = cR[thi * 32 + boff0];
-            const double b10 = cR[tlo * 32 + boff1], b11 = cR[thi * 32 + boff1];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                // A fragment order: (row g, t lo), (row g+8, t lo), (row g, t hi), (row g+8, t hi)
-                const cplx p0 = cmulc(cPsi[tlo * N1 + pnp[u][0]], cPsi[tlo * N1 + pn[u][0]]);
-                const cplx p1 = cmulc(cPsi[tlo * N1 + pnp[u][1]], cPsi[tlo * N1 + pn[u][1]]);
-                const cplx p2 = cmulc(cPsi[thi * N1 + pnp[u][0]], cPsi[thi * N1 + pn[u][0]]);
-                const cplx p3 = cmulc(cPsi[thi * N1 + pnp[u][1]], cPsi[thi * N1 + pn[u][1]]);
-                const double pr[4] = {p0.x, p1.x, p2.x, p3.x};
-                const double pi[4] = {p0.y, p1.y, p2.y, p3.y};
-                dmma16x8x8(accr[u][0], pr, b00, b01);
-                dmma16x8x8(accr[u][1], pr, b10, b11);
-                dmma16x8x8(acci[u][0], pi, b00, b01);
-                dmma16x8x8(acci[u][1], pi, b10, b11);
-            }
-        }
-        __syncthreads();
-    }
-    // epilogue: accumulator (row g + 8h, cols 2 tig, 2 tig + 1 of n-tile nt)
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (!pv[u][h]) continue;
-            const int n = pn[u][h], np = pnp[u][h];
-            auto put = [&](int i, int j, cplx v) {
-                const size_t o = (size_t)(n * NTX + i) * d.Lp + (np * NTX + j);
-                if (Gi) v = cadd(v, Gi[o]);
-                Gb[o] = v;
-            };
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                const double r0 = accr[u][nt][2 * h], r1 = accr[u][nt][2 * h + 1];
-                const double i0 = acci[u][nt][2 * h], i1 = acci[u][nt][2 * h + 1];
-                const int col = 8 * nt + 2 * tig;
-                if (col < 4) {  // two diagonal entries: (pr Rd, pi Rd)
-                    put(col, col, mk(r0, i0));
-                    put(col + 1, col + 1, mk(r1, i1));
-                } else {        // one upper pair q: U = pr Rr, W = pr Ri, Z = pi Rr, V = pi Ri
-                    const int q = (col - 4) >> 1;
-                    const int qi = (q < 3) ? 0 : (q < 5 ? 1 : 2);
-                    const int qj = (q < 3) ? q + 1 : (q < 5 ? q - 1 : 3);
-                    put(qi, qj, mk(r0 - i1, r1 + i0));
-                    put(qj, qi, mk(r0 + i1, i0 - r1));
-                }
-            }
-        }
-}
-
 // ---------------------------------------------------------------------------
-// k_gram_tma4: the same FP64 tensor-path Gram fed by the TMA engine.  The cp.async version above spends
-// only half of its warp time in the DMMA loop (profiles/r01h: 9 % issuing ~10 cp.async per thread and
-// chunk, 7 % at the two CTA barriers per chunk that couple all eight warps, 15 % in the epilogue).  The
+// k_gram_tma4: the FP64 tensor-path Gram fed by the TMA engine.  (A cp.async double-buffered predecessor spent
+// only half of its warp time in the DMMA loop, profiles/r01h: 9 % issuing ~10 cp.async per thread and
+// chunk, 7 % at the two CTA barriers per chunk that couple all eight warps, 15 % in the epilogue.)  The
 // staged operands are CONTIGUOUS in global memory -- 16 symbols of psi ([16][N+1] complex) and of R_t
 // ([16][16] complex) -- so one elected lane of a producer warp moves each chunk with two 1-D bulk copies
 // (cp.async.bulk ... mbarrier::complete_tx) into a 4-stage ring; the eight DMMA warps never touch the
@@ -734,80 +610,72 @@ static int gram_chunk(int N1, int ntx, size_t budget) {
     return tc;
 }
 
+// Shared-memory ceiling of the Gram kernels: two stages of at least 8 symbols must fit in 227 KB.  abi.cu's
+// make_dims() rejects longer phase rows with SBCE_E_UNSUPPORTED before any launch (N + 1 + n_tx^2 <= 908).
+bool gram_supports(int N1, int n_tx) { return sizeof(cplx) * (size_t)(2 * 8 * (N1 + n_tx * n_tx)) <= 227 * 1024; }
+
 template <int NTX>
 static cudaError_t run_gram_wide(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Y,
                                  const double* sm, const double* Ginit, double* Gout, const int32_t* active,
                                  cudaStream_t s) {
+    static SmemOptIn optin;
     const int P = d.N1 * (d.N1 + 1) / 2;
     dim3 grid((P + GW_PAIRS - 1) / GW_PAIRS + 1, nb);   // + 1: the right-hand-side / padding CTA
-    const int tc = gram_chunk(d.N1, NTX, 100 * 1024);
+    int tc = gram_chunk(d.N1, NTX, 100 * 1024);
+    if (sizeof(cplx) * (size_t)(2 * tc * (d.N1 + NTX * NTX)) > 227 * 1024) return cudaErrorInvalidValue;
     const int zsz = NTX * (d.n_rx > NTX ? d.n_rx : NTX);
     size_t smem = sizeof(cplx) * (size_t)(2 * tc * (d.N1 + NTX * NTX));
     const size_t smem_rhs = sizeof(cplx) * (size_t)(GR_TC * d.N1 + GR_TC * zsz);
     if (smem_rhs > smem) smem = smem_rhs;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_gram_mma<NTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
+    cudaError_t e = opt_in_smem(optin, (const void*)k_gram_mma<NTX>, smem);
+    if (e != cudaSuccess) return e;
     k_gram_mma<NTX><<<grid, GR_THREADS, smem, s>>>(d, T, tc, (const cplx*)Psi, (const cplx*)sR, (const cplx*)Y,
                                                    (const cplx*)sm, (const cplx*)Ginit, (cplx*)Gout, active);
     count_launch();
     return cudaGetLastError();
 }
 
+// n_tx <= 3: scalar Hermitian-shared kernel, chunk length shrunk for very long phase rows
 template <int NTX>
-static cudaError_t run_gram(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Y,
-                            const double* sm, const double* Ginit, double* Gout, const int32_t* active,
-                            cudaStream_t s) {
+static cudaError_t run_gram_scalar(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Y,
+                                   const double* sm, const double* Ginit, double* Gout, const int32_t* active,
+                                   cudaStream_t s) {
+    static SmemOptIn optin;
+    const int P = d.N1 * (d.N1 + 1) / 2;
+    dim3 grid((P + GR_THREADS - 1) / GR_THREADS + 1, nb);   // + 1: the right-hand-side / padding CTA
+    int tc = GR_TC;
+    while (tc > 2 && sizeof(cplx) * (size_t)(2 * tc * (d.N1 + NTX * NTX)) > 100 * 1024) tc >>= 1;
+    const int zsz = NTX * (d.n_rx > NTX ? d.n_rx : NTX);
+    size_t smem = sizeof(cplx) * (size_t)(2 * tc * (d.N1 + NTX * NTX));          // two cp.async stages (pair CTAs)
+    const size_t smem_rhs = sizeof(cplx) * (size_t)(d.N1 + zsz);                  // rhs CTA: at least one symbol
+    if (smem_rhs > smem) smem = smem_rhs;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = opt_in_smem(optin, (const void*)k_gram<NTX>, smem);
+    if (e != cudaSuccess) return e;
+    k_gram<NTX><<<grid, GR_THREADS, smem, s>>>(d, T, tc, (const cplx*)Psi, (const cplx*)sR, (const cplx*)Y,
+                                               (const cplx*)sm, (const cplx*)Ginit, (cplx*)Gout, active);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// n_tx = 4: TMA-fed tensor-path kernel while its four-stage ring fits in 160 KB (N <= 143), else the generic one
+static cudaError_t run_gram4(const Dims& d, int nb, const double* Psi, int T, const double* sR, const double* Y,
+                             const double* sm, const double* Ginit, double* Gout, const int32_t* active,
+                             cudaStream_t s) {
+    constexpr int NTX = 4;
+    static SmemOptIn optin;
+    size_t smem = sizeof(cplx) * (size_t)(GT_STAGES * GT_TC * (d.N1 + NTX * NTX));
+    if (smem > 160 * 1024) return run_gram_wide<4>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
     const int P = d.N1 * (d.N1 + 1) / 2;
     dim3 grid((P + GR_THREADS - 1) / GR_THREADS + 1, nb);   // + 1: the right-hand-side / padding CTA
     const int zsz = NTX * (d.n_rx > NTX ? d.n_rx : NTX);
-    size_t smem = sizeof(cplx) * (size_t)(2 * GR_TC * (d.N1 + NTX * NTX));          // two cp.async stages (pair CTAs)
-    const size_t smem_rhs = sizeof(cplx) * (size_t)(GR_TC * d.N1 + GR_TC * zsz);     // rhs CTA, single stage
+    const size_t smem_rhs = sizeof(cplx) * (size_t)(GR_TC * d.N1 + GR_TC * zsz);
     if (smem_rhs > smem) smem = smem_rhs;
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_gram<NTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    static int use_mma = -1;
-    if (use_mma < 0) {
-        const char* v = getenv("SBCE_GRAM_SCALAR");
-        use_mma = (v && atoi(v)) ? 0 : 1;
-    }
-    if (NTX == 4 && use_mma && sizeof(cplx) * (size_t)(2 * GM_TC * (d.N1 + NTX * NTX)) > 160 * 1024)
-        return run_gram_wide<4>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
-    static int use_tma = -1;
-    if (use_tma < 0) {
-        const char* v = getenv("SBCE_GRAM_TMA");
-        use_tma = (v && !atoi(v)) ? 0 : 1;
-    }
-    if (NTX == 4 && use_mma && use_tma) {
-        size_t smem_tma = sizeof(cplx) * (size_t)(GT_STAGES * GT_TC * (d.N1 + NTX * NTX));
-        if (smem_rhs > smem_tma) smem_tma = smem_rhs;
-        if (smem_tma > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(k_gram_tma4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
-            if (e != cudaSuccess) return e;
-        }
-        k_gram_tma4<<<grid, GT_THREADS, smem_tma, s>>>(d, T, (const cplx*)Psi, (const cplx*)sR, (const cplx*)Y,
-                                                       (const cplx*)sm, (const cplx*)Ginit, (cplx*)Gout, active);
-        count_launch();
-        return cudaGetLastError();
-    }
-    if (NTX == 4 && use_mma) {
-        const size_t smem_mma = sizeof(cplx) * (size_t)(2 * GM_TC * (d.N1 + NTX * NTX));
-        if (smem_mma > smem) smem = smem_mma;
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(k_gram_mma4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
-        k_gram_mma4<<<grid, GR_THREADS, smem, s>>>(d, T, (const cplx*)Psi, (const cplx*)sR, (const cplx*)Y,
-                                                   (const cplx*)sm, (const cplx*)Ginit, (cplx*)Gout, active);
-    } else {
-        k_gram<NTX><<<grid, GR_THREADS, smem, s>>>(d, T, (const cplx*)Psi, (const cplx*)sR, (const cplx*)Y,
-                                                   (const cplx*)sm, (const cplx*)Ginit, (cplx*)Gout, active);
-    }
+    cudaError_t e = opt_in_smem(optin, (const void*)k_gram_tma4, smem);
+    if (e != cudaSuccess) return e;
+    k_gram_tma4<<<grid, GT_THREADS, smem, s>>>(d, T, (const cplx*)Psi, (const cplx*)sR, (const cplx*)Y,
+                                               (const cplx*)sm, (const cplx*)Ginit, (cplx*)Gout, active);
     count_launch();
     return cudaGetLastError();
 }
@@ -818,10 +686,10 @@ cudaError_t launch_normal_equations(const Dims& d, int nb, const double* Psi, in
                                     const int32_t* active, cudaStream_t s) {
     if (d.n_rx > RH_MAXR) return cudaErrorInvalidValue;
     switch (d.n_tx) {
-        case 1: return run_gram<1>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
-        case 2: return run_gram<2>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
-        case 3: return run_gram<3>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
-        case 4: return run_gram<4>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
+        case 1: return run_gram_scalar<1>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
+        case 2: return run_gram_scalar<2>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
+        case 3: return run_gram_scalar<3>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
+        case 4: return run_gram4(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
         case 5: return run_gram_wide<5>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
         case 6: return run_gram_wide<6>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
         case 7: return run_gram_wide<7>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
@@ -837,352 +705,21 @@ constexpr int CH_NB = 16;            // panel width
 constexpr int CH_DS = CH_NB + 1;     // row stride (complex) of the shared 16x16 blocks
 
 
-// LEFT-looking blocked complex Cholesky on the FP64 tensor path (mma.sync m16n8k8.f64, SASS DMMA).
-// Per 16-column panel k, three phases separated by CTA barriers:
-//   1. every warp brings its 16-row tiles up to date with ALL previous panels in one
-//      register-accumulated product   S = A - C[rows, 0:k0] * C[k0:k0+16, 0:k0]^H
-//      (operand fragments are 16-byte complex loads straight from the L2/L1-resident factor,
-//      8 DMMAs per 8 previous columns) and writes S back in place;
-//   2. warp 0 factors the 16x16 diagonal block D and forms W = D^-1 in shared memory;
-//   3. every warp finishes its tiles below the diagonal block with one more product X = S W^H
-//      (16 DMMAs per tile) -- the triangular solve as a tensor-core GEMM -- and writes X once.
-// The trailing matrix is never touched; the B^H rows carried under the matrix come out as
-// (C^-1 B)^H, i.e. the forward substitution is free.  Only 9 KB of shared memory per CTA, so four
-// CTAs (trials) share an SM and overlap each other's serial phase 2.
-template <int CH_THREADS, int CH_MINB>
-__global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol(Dims d, cplx* __restrict__ Gall,
-                                                              cplx* __restrict__ theta,
-                                                              const int32_t* __restrict__ active,
-                                                              int32_t* __restrict__ stat, cplx* th_global) {
-    constexpr int CH_WARPS = CH_THREADS / 32;
-    extern __shared__ double2 csm[];
-    const int b = blockIdx.x;
-    if (active != nullptr && active[b] == 0) return;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, tig = lane & 3;
-    const int Lp = d.Lp, Ltot = d.Ltot, ld = d.Lp;
-    cplx* A = Gall + (size_t)b * Ltot * Lp;
-
-    cplx* sD = csm;                   // [16][17] diagonal block factor (later: reduction scratch)
-    cplx* sW = sD + CH_NB * CH_DS;    // [16][17] its inverse
-    // [Lp][n_rx] solution during the back substitution: shared memory, or (very long channels) a
-    // per-trial global scratch -- CTA barriers order its accesses just the same
-    cplx* th = th_global ? th_global + (size_t)b * d.Lp * d.n_rx : sW + CH_NB * CH_DS;
-    __shared__ int s_bad, s_next1, s_next3;
-    if (tid == 0) { s_bad = 0; s_next1 = 1; s_next3 = 0; }
-
-    double maxpiv = 0.0;   // warp 0: largest pivot so far (uniform across its lanes)
-    for (int k0 = 0; k0 < Lp; k0 += CH_NB) {
-        const int nb = min(CH_NB, Lp - k0);   // multiple of 4
-        const int rows = Ltot - k0;           // rows of the panel including its diagonal block
-        const int nrt = (rows + 15) >> 4;
-        __syncthreads();                      // previous panel fully written; tile counters reset
-        if (tid == 0) s_next3 = 0;            // phase-3 counter: idle between this barrier and the next one
-        // ---- phase 1: S = A - C_prev C_rows^H for every 16-row tile.  Tile 0 (the diagonal block) belongs to
-        // warp 0, which then goes straight on to phase 2 while the other warps keep claiming tiles from a shared
-        // counter (warp 0 joins them afterwards): the serial factorisation overlaps the panel update.
-        auto phase1_tile = [&](int rt) {
-            {
-                const int r0 = rt << 4;
-                double cr[2][4], ci[2][4];
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { cr[j][e] = 0.0; ci[j][e] = 0.0; }
-                const int ra = min(r0 + g, rows - 1), rb8 = min(r0 + g + 8, rows - 1);
-                const cplx* pa0 = A + (size_t)(k0 + ra) * ld + tig;
-                const cplx* pa1 = A + (size_t)(k0 + rb8) * ld + tig;
-                const cplx* pb0 = A + (size_t)min(k0 + g, Ltot - 1) * ld + tig;
-                const cplx* pb1 = A + (size_t)min(k0 + 8 + g, Ltot - 1) * ld + tig;
-                // the panel block itself is only needed at the very end (S = A - acc): start fetching it now
-                if (tig == 0) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)(k0 + ra) * ld + k0));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)(k0 + ra) * ld + k0 + 8));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)(k0 + rb8) * ld + k0));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)(k0 + rb8) * ld + k0 + 8));
-                }
-#pragma unroll 2
-                for (int q0 = 0; q0 < k0; q0 += 8) {
-                    const cplx a0 = pa0[q0], a1 = pa1[q0], a2 = pa0[q0 + 4], a3 = pa1[q0 + 4];
-                    const cplx b00 = pb0[q0], b01 = pb0[q0 + 4], b10 = pb1[q0], b11 = pb1[q0 + 4];
-                    const double ar[4] = {a0.x, a1.x, a2.x, a3.x};
-                    const double ai[4] = {a0.y, a1.y, a2.y, a3.y};
-                    // sum_q a conj(b):  re += ar br + ai bi ;  im += ai br - ar bi
-                    dmma16x8x8(cr[0], ar, b00.x, b01.x);
-                    dmma16x8x8(cr[0], ai, b00.y, b01.y);
-                    dmma16x8x8(ci[0], ai, b00.x, b01.x);
-                    dmma16x8x8(ci[0], ar, -b00.y, -b01.y);
-                    dmma16x8x8(cr[1], ar, b10.x, b11.x);
-                    dmma16x8x8(cr[1], ai, b10.y, b11.y);
-                    dmma16x8x8(ci[1], ai, b10.x, b11.x);
-                    dmma16x8x8(ci[1], ar, -b10.y, -b11.y);
-                }
-                // in place: fragment rows g / g+8, columns 8j + 2 tig + {0,1}
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int lr = r0 + g + 8 * h;
-                        const int c = 8 * j + 2 * tig;
-                        if (lr < rows && c < nb) {
-                            cplx* p2 = A + (size_t)(k0 + lr) * ld + k0 + c;
-                            const cplx v0 = p2[0], v1 = p2[1];
-                            p2[0] = mk(v0.x - cr[j][2 * h], v0.y - ci[j][2 * h]);
-                            p2[1] = mk(v1.x - cr[j][2 * h + 1], v1.y - ci[j][2 * h + 1]);
-                        }
-                    }
-            }
-        };
-        auto claim = [&](int* counter) {
-            int v = 0;
-            if (lane == 0) v = atomicAdd(counter, 1);
-            return __shfl_sync(0xffffffffu, v, 0);
-        };
-        if (warp == 0) {
-            if (k0 > 0) phase1_tile(0);
-            __syncwarp();
-        } else if (k0 > 0) {
-            for (int rt = claim(&s_next1); rt < nrt; rt = claim(&s_next1)) phase1_tile(rt);
-        }
-        // ---- phase 2: diagonal block -> sD, unblocked Cholesky by warp 0 (lane = row), W = D^-1
-        if (warp == 0) {
-            __threadfence_block();
-            const int r = lane;
-            for (int c = 0; c < CH_NB; ++c)
-                if (r < CH_NB) sD[r * CH_DS + c] = (r < nb && c <= r && c < nb) ? A[(size_t)(k0 + r) * ld + k0 + c] : mk(0.0, 0.0);
-            __syncwarp();
-            for (int c = 0; c < nb; ++c) {
-                double piv = sD[c * CH_DS + c].x;
-                // numerically singular: non-positive, or below 1e-13 of the largest pivot so far (an exactly
-                // rank-deficient matrix leaves rounding noise of either sign here); identity padding exempt
-                if (!(piv > ((k0 + c < d.L) ? 1e-13 * maxpiv : 0.0))) {
-                    if (r == 0) s_bad = 1;
-                    piv = 1.0;
-                }
-                maxpiv = fmax(maxpiv, piv);
-                const double dg = sqrt(piv);
-                const double inv = 1.0 / dg;
-                __syncwarp();
-                if (r == c) sD[c * CH_DS + c] = mk(dg, 0.0);
-                if (r > c && r < nb) sD[r * CH_DS + c] = cscale(sD[r * CH_DS + c], inv);
-                __syncwarp();
-                if (r > c && r < nb) {
-                    const cplx lrc = sD[r * CH_DS + c];
-                    for (int q = c + 1; q <= r; ++q) cfmsc(sD[r * CH_DS + q], lrc, sD[q * CH_DS + c]);
-                }
-                __syncwarp();
-            }
-            // W = D^-1 (lower triangular), lane = column; rows/cols >= nb are zero
-            if (r < CH_NB) {
-                const int c = r;
-                for (int i = 0; i < CH_NB; ++i) {
-                    cplx v = mk(0.0, 0.0);
-                    if (c < nb && i < nb) {
-                        if (i == c) v = mk(1.0 / sD[i * CH_DS + i].x, 0.0);
-                        else if (i > c) {
-                            cplx a0 = mk(0.0, 0.0), a1 = mk(0.0, 0.0);
-                            int q = c;
-                            for (; q + 1 < i; q += 2) {
-                                cfma(a0, sD[i * CH_DS + q], sW[q * CH_DS + c]);
-                                cfma(a1, sD[i * CH_DS + q + 1], sW[(q + 1) * CH_DS + c]);
-                            }
-                            if (q < i) cfma(a0, sD[i * CH_DS + q], sW[q * CH_DS + c]);
-                            const double invd = -1.0 / sD[i * CH_DS + i].x;
-                            v = mk((a0.x + a1.x) * invd, (a0.y + a1.y) * invd);
-                        }
-                    }
-                    sW[i * CH_DS + c] = v;
-                }
-            }
-            __syncwarp();
-            // factored diagonal block back to global
-            for (int e = lane; e < nb * nb; e += 32) {
-                const int rr = e / nb, c = e % nb;
-                if (c <= rr) A[(size_t)(k0 + rr) * ld + k0 + c] = sD[rr * CH_DS + c];
-            }
-        }
-        if (warp == 0 && k0 > 0) {
-            for (int rt = claim(&s_next1); rt < nrt; rt = claim(&s_next1)) phase1_tile(rt);
-        }
-        __syncthreads();
-        if (tid == 0) s_next1 = 1;            // phase-1 counter (tile 0 is reserved for warp 0)
-        // ---- phase 3: rows below the diagonal block: X = S W^H, i.e. X[r][c] = sum_q S[r][q] conj(W[c][q])
-        // local row tiles start at local row nb (nb < 16 only in the last panel, where the tile grid shifts)
-        {
-            const int rows3 = rows - nb;
-            const int nrt3 = (rows3 + 15) >> 4;
-            for (int rt = claim(&s_next3); rt < nrt3; rt = claim(&s_next3)) {
-                const int r0 = nb + (rt << 4);
-                const int ra = min(r0 + g, rows - 1), rb8 = min(r0 + g + 8, rows - 1);
-                const cplx* pa0 = A + (size_t)(k0 + ra) * ld + k0 + tig;
-                const cplx* pa1 = A + (size_t)(k0 + rb8) * ld + k0 + tig;
-                double cr[2][4], ci[2][4];
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { cr[j][e] = 0.0; ci[j][e] = 0.0; }
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    // columns q = 8kk + tig, +4 of S (zero beyond nb: they were never part of this panel)
-                    const int q0 = 8 * kk + tig;
-                    cplx a0 = mk(0, 0), a1 = mk(0, 0), a2 = mk(0, 0), a3 = mk(0, 0);
-                    if (q0 < nb) { a0 = pa0[8 * kk]; a1 = pa1[8 * kk]; }
-                    if (q0 + 4 < nb) { a2 = pa0[8 * kk + 4]; a3 = pa1[8 * kk + 4]; }
-                    const double ar[4] = {a0.x, a1.x, a2.x, a3.x};
-                    const double ai[4] = {a0.y, a1.y, a2.y, a3.y};
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        // B[k=q][n=c] = conj(W[c][q]), c = 8j + g, q = 8kk + tig (+4)
-                        const cplx w0 = sW[(8 * j + g) * CH_DS + 8 * kk + tig];
-                        const cplx w1 = sW[(8 * j + g) * CH_DS + 8 * kk + tig + 4];
-                        dmma16x8x8(cr[j], ar, w0.x, w1.x);
-                        dmma16x8x8(cr[j], ai, w0.y, w1.y);
-                        dmma16x8x8(ci[j], ai, w0.x, w1.x);
-                        dmma16x8x8(ci[j], ar, -w0.y, -w1.y);
-                    }
-                }
-                __syncwarp();  // all lanes have read S before anyone overwrites it
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int lr = r0 + g + 8 * h;
-                        const int c = 8 * j + 2 * tig;
-                        if (lr < rows && c < nb) {
-                            cplx* p2 = A + (size_t)(k0 + lr) * ld + k0 + c;
-                            p2[0] = mk(cr[j][2 * h], ci[j][2 * h]);
-                            p2[1] = mk(cr[j][2 * h + 1], ci[j][2 * h + 1]);
-                        }
-                    }
-            }
-        }
-    }
-    __syncthreads();
-    if (tid == 0 && s_bad && stat) atomicOr(&stat[b], SBCE_ST_NOT_PD);
-
-    // ---- back substitution  C^H theta = z,  z[l][r] = conj(A[Lp + r][l])
-    // Column-oriented ("right-looking"): blocks from the bottom up; once the 16 unknowns of a block are
-    // known, every earlier right-hand-side entry c < k0 is updated with the block's 16 factor rows --
-    // those rows are contiguous in memory, so consecutive threads read consecutive columns (coalesced)
-    // and each thread has 16 independent loads in flight.
-    const int nrx = d.n_rx;
-    for (int e = tid; e < Lp * nrx; e += CH_THREADS) {
-        const int l = e / nrx, r = e % nrx;
-        th[e] = cconj(A[(size_t)(Lp + r) * ld + l]);
-    }
-    for (int k0 = ((Lp - 1) / CH_NB) * CH_NB; k0 >= 0; k0 -= CH_NB) {
-        const int nb = min(CH_NB, Lp - k0);
-        __syncthreads();  // th updates of the previous block are complete
-        for (int e = tid; e < nb * nb; e += CH_THREADS) {
-            const int r = e / nb, c = e % nb;
-            sD[r * CH_DS + c] = (c <= r) ? A[(size_t)(k0 + r) * ld + k0 + c] : mk(0.0, 0.0);
-        }
-        __syncthreads();
-        // D^H x = rhs, upper triangular, one thread per right-hand side
-        if (tid < nrx) {
-            const int r = tid;
-            for (int c = nb - 1; c >= 0; --c) {
-                cplx v = th[(k0 + c) * nrx + r];
-                for (int q = c + 1; q < nb; ++q) cfmsc(v, th[(k0 + q) * nrx + r], sD[q * CH_DS + c]);
-                th[(k0 + c) * nrx + r] = cscale(v, 1.0 / sD[c * CH_DS + c].x);
-            }
-        }
-        __syncthreads();
-        // th[c][:] -= sum_q conj(C[k0+q][c]) x[q][:]   for all c < k0
-        for (int c = tid; c < k0; c += CH_THREADS) {
-            cplx cq[CH_NB];
-#pragma unroll
-            for (int q = 0; q < CH_NB; ++q) cq[q] = (q < nb) ? A[(size_t)(k0 + q) * ld + c] : mk(0.0, 0.0);
-            for (int r = 0; r < nrx; ++r) {
-                cplx v = th[c * nrx + r];
-#pragma unroll
-                for (int q = 0; q < CH_NB; ++q)
-                    if (q < nb) cfmsc(v, th[(k0 + q) * nrx + r], cq[q]);  // v -= x_q conj(C[k0+q][c])
-                th[c * nrx + r] = v;
-            }
-        }
-    }
-    __syncthreads();
-    cplx* out = theta + (size_t)b * d.L * nrx;
-    bool bad = false;
-    for (int e = tid; e < d.L * nrx; e += CH_THREADS) {
-        const cplx v = th[e];
-        out[e] = v;
-        if (!isfinite(v.x) || !isfinite(v.y)) bad = true;
-    }
-    if (bad && stat) atomicOr(&stat[b], SBCE_ST_NONFINITE);
-}
-
-// ---------------------------------------------------------------------------
-// k_chol2: the same left-looking DMMA Cholesky with LOOK-AHEAD.  Profiling k_chol (profiles/r01h) showed
-// 28 % of the warp samples at the two CTA barriers per panel (the other warps wait for warp 0's serial
-// diagonal factorisation, and the four co-resident CTAs run in lock-step so nobody fills the pipe) and
-// 33 % on the first DMMA after each batch of global loads.  Here an iteration k works on row tiles below
-// the diagonal block of panel k, and every tile is taken through TWO steps by the warp that claimed it:
-//   A. X = S W_k^H            (triangular solve of panel k as a GEMM, 16 DMMA quads), then
+// k_chol2: LEFT-looking blocked complex Cholesky (panel width 16) on the FP64 tensor path (mma.sync
+// m16n8k8.f64, SASS DMMA) with LOOK-AHEAD.  Iteration k works on the 16-row tiles below the diagonal block of
+// panel k, and every tile is taken through TWO steps by the warp that claimed it:
+//   A. X = S W_k^H            (triangular solve of panel k as a GEMM against the inverse of the diagonal
+//                              block, 16 DMMA quads), then
 //   B. S' = A - C[rows, 0:g0] C[g0:g0+16, 0:g0]^H   (update for panel k+1 against ALL previous columns,
 //      operand fragments double-buffered in registers so the loads of step q+1 are in flight during the
 //      DMMAs of step q).
 // Warp 0 takes tile 0 -- the next diagonal block row -- first, publishes "block row ready" through a
 // shared flag (the other warps need its freshly solved columns as the B operand of step B), then factors
 // the next diagonal block and its inverse W_{k+1} into the other shared buffer while the other warps chew
-// through the remaining tiles.  One CTA barrier per panel instead of two, and the serial part is hidden
-// behind tile work in all but the first and last panels.
+// through the remaining tiles: one CTA barrier per panel.  The trailing matrix is never touched; the B^H
+// rows carried under the matrix come out as (C^-1 B)^H, i.e. the forward substitution is free.  (Its
+// two-barrier predecessor with a shared-memory diagonal factor is documented in profiles/r01h-r01j.)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void chol_diag_factor(const Dims& d, cplx* A, int ld, int k0, int nb, cplx* sD, cplx* sW,
-                                                 int lane, double& maxpiv, int* s_bad) {
-    const int r = lane;
-    for (int c = 0; c < CH_NB; ++c)
-        if (r < CH_NB) sD[r * CH_DS + c] = (r < nb && c <= r && c < nb) ? A[(size_t)(k0 + r) * ld + k0 + c] : mk(0.0, 0.0);
-    __syncwarp();
-    for (int c = 0; c < nb; ++c) {
-        double piv = sD[c * CH_DS + c].x;
-        // numerically singular: non-positive, or below 1e-13 of the largest pivot so far; identity padding exempt
-        if (!(piv > ((k0 + c < d.L) ? 1e-13 * maxpiv : 0.0))) {
-            if (r == 0) *s_bad = 1;
-            piv = 1.0;
-        }
-        maxpiv = fmax(maxpiv, piv);
-        const double dg = sqrt(piv);
-        const double inv = 1.0 / dg;
-        __syncwarp();
-        if (r == c) sD[c * CH_DS + c] = mk(dg, 0.0);
-        if (r > c && r < nb) sD[r * CH_DS + c] = cscale(sD[r * CH_DS + c], inv);
-        __syncwarp();
-        if (r > c && r < nb) {
-            const cplx lrc = sD[r * CH_DS + c];
-            for (int q = c + 1; q <= r; ++q) cfmsc(sD[r * CH_DS + q], lrc, sD[q * CH_DS + c]);
-        }
-        __syncwarp();
-    }
-    // W = D^-1 (lower triangular), lane = column; rows/cols >= nb are zero
-    if (r < CH_NB) {
-        const int c = r;
-        for (int i = 0; i < CH_NB; ++i) {
-            cplx v = mk(0.0, 0.0);
-            if (c < nb && i < nb) {
-                if (i == c) v = mk(1.0 / sD[i * CH_DS + i].x, 0.0);
-                else if (i > c) {
-                    cplx a0 = mk(0.0, 0.0), a1 = mk(0.0, 0.0);
-                    int q = c;
-                    for (; q + 1 < i; q += 2) {
-                        cfma(a0, sD[i * CH_DS + q], sW[q * CH_DS + c]);
-                        cfma(a1, sD[i * CH_DS + q + 1], sW[(q + 1) * CH_DS + c]);
-                    }
-                    if (q < i) cfma(a0, sD[i * CH_DS + q], sW[q * CH_DS + c]);
-                    const double invd = -1.0 / sD[i * CH_DS + i].x;
-                    v = mk((a0.x + a1.x) * invd, (a0.y + a1.y) * invd);
-                }
-            }
-            sW[i * CH_DS + c] = v;
-        }
-    }
-    __syncwarp();
-    for (int e = lane; e < nb * nb; e += 32) {   // factored diagonal block back to global
-        const int rr = e / nb, c = e % nb;
-        if (c <= rr) A[(size_t)(k0 + rr) * ld + k0 + c] = sD[rr * CH_DS + c];
-    }
-}
 
 // Diagonal block of the look-ahead kernel, register resident.  Profiling (profiles/r01i) showed the
 // shared-memory version above on warp 0's critical path for 43 % of the kernel: ~55k cycles per panel of
@@ -1261,8 +798,7 @@ template <int CH_THREADS, int CH_MINB>
 __global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol2(Dims d, cplx* __restrict__ Gall,
                                                                cplx* __restrict__ theta,
                                                                const int32_t* __restrict__ active,
-                                                               int32_t* __restrict__ stat, cplx* th_global,
-                                                               int pf_cols, int stagger_ns) {
+                                                               int32_t* __restrict__ stat, cplx* th_global) {
     extern __shared__ double2 csm[];
     const int b = blockIdx.x;
     if (active != nullptr && active[b] == 0) return;
@@ -1270,10 +806,6 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol2(Dims d, cplx* __r
     const int g = lane >> 2, tig = lane & 3;
     const int Lp = d.Lp, Ltot = d.Ltot, ld = d.Lp;
     cplx* A = Gall + (size_t)b * Ltot * Lp;
-    if (stagger_ns > 0) {   // de-phase the co-resident CTAs of an SM (they would otherwise hit their serial parts together)
-        const int slot = (blockIdx.x / 148) & 3;
-        for (int i = 0; i < slot; ++i) __nanosleep(stagger_ns);
-    }
 
     cplx* sD = csm;                       // [16][17] diagonal block being factored (later: back substitution)
     cplx* sWb = sD + CH_NB * CH_DS;       // [2][16][17] inverse of the diagonal block, double buffered
@@ -1378,10 +910,6 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol2(Dims d, cplx* __r
                 for (int q0 = 0; q0 < g0; q0 += 8) {
                     cplx na[4], nbq[4];
                     const int qn = (q0 + 8 < g0) ? q0 + 8 : q0;   // last step reloads itself (harmless, L1 hit)
-                    if (pf_cols > 0 && tig == 0 && q0 + pf_cols < g0) {   // pull the lines of a later step into L2
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pa0 + q0 + pf_cols));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pa1 + q0 + pf_cols));
-                    }
                     na[0] = pa0[qn]; na[1] = pa1[qn]; na[2] = pa0[qn + 4]; na[3] = pa1[qn + 4];
                     nbq[0] = pb0[qn]; nbq[1] = pb0[qn + 4]; nbq[2] = pb1[qn]; nbq[3] = pb1[qn + 4];
                     const double ar[4] = {fa[0].x, fa[1].x, fa[2].x, fa[3].x};
@@ -1477,38 +1005,11 @@ __global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol2(Dims d, cplx* __r
 template <int T, int MB>
 static cudaError_t run_chol2(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
                              size_t smem, double* thg, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(k_chol2<T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static SmemOptIn optin;
+    cudaError_t e = opt_in_smem(optin, (const void*)k_chol2<T, MB>, smem);
     if (e != cudaSuccess) return e;
-    static int pf = -1, stag = -1;
-    if (pf < 0) {
-        const char* v = getenv("SBCE_CHOL_PF");
-        pf = v ? atoi(v) : 0;
-        v = getenv("SBCE_CHOL_STAGGER");
-        stag = v ? atoi(v) : 0;
-    }
-    k_chol2<T, MB><<<nb, T, smem, s>>>(d, (cplx*)G, (cplx*)theta, active, stat, (cplx*)thg, pf, stag);
+    k_chol2<T, MB><<<nb, T, smem, s>>>(d, (cplx*)G, (cplx*)theta, active, stat, (cplx*)thg);
     count_launch();
-    return cudaGetLastError();
-}
-
-template <int T, int MB>
-static cudaError_t run_chol(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
-                            size_t smem, double* thg, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(k_chol<T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    static int wave = -1;
-    if (wave < 0) {
-        const char* v = getenv("SBCE_CHOL_WAVE");
-        wave = v ? atoi(v) : 0;
-    }
-    const int step = wave > 0 ? wave : nb;
-    for (int b0 = 0; b0 < nb; b0 += step) {
-        const int n = (nb - b0 < step) ? nb - b0 : step;
-        k_chol<T, MB><<<n, T, smem, s>>>(d, (cplx*)G + (size_t)b0 * d.Ltot * d.Lp, (cplx*)theta + (size_t)b0 * d.L * d.n_rx,
-                                         active ? active + b0 : nullptr, stat ? stat + b0 : nullptr,
-                                         thg ? (cplx*)thg + (size_t)b0 * d.Lp * d.n_rx : nullptr);
-        count_launch();
-    }
     return cudaGetLastError();
 }
 
@@ -1522,16 +1023,9 @@ cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, c
         thg = th_scratch;
         smem = sizeof(cplx) * (3 * CH_NB * CH_DS);
     }
-    // SBCE_CHOL_VARIANT=1 selects the predecessor kernel (two barriers per panel, shared-memory diagonal factor)
-    // for A/B runs.  CTA shapes measured on B200 (N=64, 4x4: L=260, 592 trials) for the look-ahead kernel:
+    // CTA shapes measured on B200 (N=64, 4x4: L=260, 592 trials) for the look-ahead kernel:
     // 128 threads x 4 CTAs/SM 0.98 ms, 96 x 5 1.27 ms, 256 x 2 1.57 ms, 160 x 3 1.45 ms, 128 x 5 (96 registers)
     // 1.11 ms -- latency bound, more resident trials per SM win even though their factors no longer fit in L2.
-    static int variant = -1;
-    if (variant < 0) {
-        const char* v = getenv("SBCE_CHOL_VARIANT");
-        variant = v ? atoi(v) : 0;
-    }
-    if (variant == 1) return run_chol<128, 4>(d, nb, G, theta, active, stat, smem, thg, s);
     return run_chol2<128, 4>(d, nb, G, theta, active, stat, smem, thg, s);
 }
 

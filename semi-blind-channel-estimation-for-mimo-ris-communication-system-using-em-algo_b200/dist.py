@@ -57,7 +57,12 @@ def allreduce_sum(acc: np.ndarray, device=None) -> np.ndarray:
 
     t = torch.from_numpy(np.ascontiguousarray(acc, dtype=np.float64))
     if dist.get_backend() == "nccl":
-        t = t.cuda() if device is None else t.to(device)
+        # the rank's own GPU: an int is a CUDA ordinal; None falls back to the current device
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        elif isinstance(device, int):
+            device = torch.device("cuda", device)
+        t = t.to(device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.cpu().numpy()
 

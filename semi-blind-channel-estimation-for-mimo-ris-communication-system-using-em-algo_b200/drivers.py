@@ -64,6 +64,9 @@ class PointResult:
                          self.ser_coded_sum, self.n_trials], dtype=np.float64)
 
 
+SER_MODES = ("soft", "hard", "zf", "mmse")
+
+
 def cuda_runner(prob: engine.Problem, tb: signal_model.TrialBatch, device=0) -> engine.Result:
     """Default runner: the CUDA library through its host-buffer entry point."""
     theta0 = None if prob.zero_start else tb.theta0
@@ -113,7 +116,7 @@ def run_point_device(cfg: SweepConfig, point_index: int, device=0, per_trial=Non
                           h_true=tb["h"])
             if st0 is not None:
                 res.status.bitwise_or_(st0)   # a rank-deficient pilot block flags the trial
-            ses.accumulate(res, tb["Xd"], acc_n, acc_s if cfg.mode in ("soft", "hard", "zf", "mmse") else None)
+            ses.accumulate(res, tb["Xd"], acc_n, acc_s if cfg.mode in SER_MODES else None)
             if per_trial is not None:
                 per_trial[b0:b0 + nb] = res.nmse.cpu().numpy()
             acc.n_trials += nb
@@ -149,7 +152,9 @@ def run_point(cfg: SweepConfig, point_index: int, runner: Callable = None, devic
         acc.n_trials += nb
         if per_trial is not None:
             per_trial[b0:b0 + nb] = nm
-        if res.kstar is not None:
+        # joint decisions exist in the exhaustive and detector modes only: the partitioned estimators
+        # (PM.py / PM_beta.py) never decide the whole symbol vector, kstar is -1 there
+        if res.kstar is not None and cfg.mode in SER_MODES:
             xest = symbols_of(np.asarray(res.kstar), cfg.M, cfg.n_tx)
             acc.sym_err += float(np.count_nonzero(tb.Xd - xest))
             acc.sym_total += float(tb.Xd.size)
@@ -158,14 +163,18 @@ def run_point(cfg: SweepConfig, point_index: int, runner: Callable = None, devic
 
 
 def _finish(xs, accs: List[PointResult], per_trial=None, device=None):
+    """Cross-rank sum of the per-point accumulators (the one collective of a sweep, SNR/all_Detectors.py:389-395
+    averages over trials) and the averaged curves.  Points without symbol decisions report ser = NaN."""
     mat = np.stack([a.vec() for a in accs])
     mat = dist.allreduce_sum(mat, device=device)
-    out = dict(x=list(xs),
-               nmse=mat[:, 0] / np.maximum(mat[:, 1], 1.0),
-               n_valid=mat[:, 1], n_flagged=mat[:, 2],
-               ser=mat[:, 3] / np.maximum(mat[:, 4], 1.0),
-               ser_as_coded=mat[:, 5] / np.maximum(mat[:, 6], 1.0),
-               n_trials=mat[:, 6])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        has_ser = mat[:, 4] > 0
+        out = dict(x=list(xs),
+                   nmse=mat[:, 0] / np.maximum(mat[:, 1], 1.0),
+                   n_valid=mat[:, 1], n_flagged=mat[:, 2],
+                   ser=np.where(has_ser, mat[:, 3] / np.maximum(mat[:, 4], 1.0), np.nan),
+                   ser_as_coded=np.where(has_ser, mat[:, 5] / np.maximum(mat[:, 6], 1.0), np.nan),
+                   n_trials=mat[:, 6])
     if per_trial is not None:
         out["per_trial"] = per_trial
     return out
@@ -179,7 +188,7 @@ def _sweep(cfg: SweepConfig, xs: Sequence, apply: Callable, runner=None, device=
         c = apply(cfg, x)
         col = None if per is None else per[:, i]
         accs.append(run_point(c, i, runner, device, col))
-    return _finish(xs, accs, per, device=None)
+    return _finish(xs, accs, per, device=device)
 
 
 def nmse_vs_tp(cfg: SweepConfig, T_p_list: Sequence[int], runner=None, device=0, keep_per_trial=False):

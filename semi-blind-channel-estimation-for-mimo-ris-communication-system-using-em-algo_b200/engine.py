@@ -231,6 +231,10 @@ class DeviceSession:
         self.ws_bytes = workspace_bytes(prob, self.trials_in_flight)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
 
+    def _on_device(self):
+        """libsbce launches on the calling thread's CURRENT device: make it the session's for the call."""
+        return self.torch.cuda.device(self.device)
+
     def _check(self, t, shape, name, dtype):
         torch = self.torch
         if t is None:
@@ -282,15 +286,19 @@ class DeviceSession:
         io.iters = _t_ptr(out.iters)
         io.status = _t_ptr(out.status)
         cfg = p.cfg(B)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(self.lib.sbce_em_batch(C.byref(cfg), C.byref(io), self.ws.data_ptr(), self.ws_bytes, stream))
+        with self._on_device():
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.sbce_em_batch(C.byref(cfg), C.byref(io), self.ws.data_ptr(), self.ws_bytes, stream))
         return out
 
-    def estep(self, Yd, PsiD, theta, varn):
-        """Stand-alone E-step sweep at `theta` -> (m, R, kstar, lse_sym) device tensors."""
+    def estep(self, Yd, PsiD, theta, varn, Xp=None):
+        """Stand-alone E-step sweep at `theta` -> (m, R, kstar, lse_sym) device tensors.
+        With Problem.superimposed the per-symbol pilot offsets Xp [B][T_d][n_tx] are required."""
         torch, p = self.torch, self.prob
         B = int(Yd.shape[0])
-        io = self._io(B, Yd, None, PsiD, None, None, varn, None, None, None)
+        if p.superimposed and Xp is None:
+            raise ValueError("superimposed pilots: estep() needs the offsets Xp [B][T_d][n_tx]")
+        io = self._io(B, Yd, None, PsiD, None, Xp if p.superimposed else None, varn, None, None, None)
         dev = self.device
         m = torch.empty((B, p.T_d, p.n_tx), dtype=torch.complex128, device=dev)
         R = torch.empty((B, p.T_d, p.n_tx, p.n_tx), dtype=torch.complex128, device=dev)
@@ -298,9 +306,10 @@ class DeviceSession:
         ls = torch.empty((B, p.T_d), dtype=torch.float64, device=dev)
         self._check(theta, (B, p.L, p.n_rx), "theta", torch.complex128)
         cfg = p.cfg(B)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(self.lib.sbce_estep(C.byref(cfg), C.byref(io), theta.data_ptr(), m.data_ptr(), R.data_ptr(),
-                                       ks.data_ptr(), ls.data_ptr(), self.ws.data_ptr(), self.ws_bytes, stream))
+        with self._on_device():
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self.lib.sbce_estep(C.byref(cfg), C.byref(io), theta.data_ptr(), m.data_ptr(), R.data_ptr(),
+                                           ks.data_ptr(), ls.data_ptr(), self.ws.data_ptr(), self.ws_bytes, stream))
         return m, R, ks, ls
 
     def mstep(self, Yd, Yp, PsiD, PsiP, Xp, stat_m, stat_R):
@@ -315,9 +324,10 @@ class DeviceSession:
         theta = torch.empty((B, p.L, p.n_rx), dtype=torch.complex128, device=dev)
         status = torch.empty((B,), dtype=torch.int32, device=dev)
         cfg = p.cfg(B)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(self.lib.sbce_mstep(C.byref(cfg), C.byref(io), stat_m.data_ptr(), stat_R.data_ptr(),
-                                       theta.data_ptr(), status.data_ptr(), self.ws.data_ptr(), self.ws_bytes, stream))
+        with self._on_device():
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self.lib.sbce_mstep(C.byref(cfg), C.byref(io), stat_m.data_ptr(), stat_R.data_ptr(),
+                                           theta.data_ptr(), status.data_ptr(), self.ws.data_ptr(), self.ws_bytes, stream))
         return theta, status
 
 
@@ -345,8 +355,9 @@ class DeviceSession:
         g.pilot_design, g.data_phases, g.varh = _lib.PILOTS[pilot_design], _lib.PHASES_KIND[data_phases], float(varh)
         g.no_direct_link = 0 if direct_link else 1   # all Problem.N + 1 phase rows are RIS elements
         cfg = p.cfg(B)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(self.lib.sbce_generate_batch(C.byref(cfg), C.byref(g), C.byref(io), stream))
+        with self._on_device():
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self.lib.sbce_generate_batch(C.byref(cfg), C.byref(g), C.byref(io), stream))
         return tb
 
     def ls_start(self, Yp, PsiP, Xp):
@@ -362,9 +373,10 @@ class DeviceSession:
         theta0 = torch.empty((B, p.L, p.n_rx), dtype=torch.complex128, device=dev)
         status = torch.empty((B,), dtype=torch.int32, device=dev)
         cfg = p.cfg(B)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(self.lib.sbce_ls_start(C.byref(cfg), C.byref(io), theta0.data_ptr(), status.data_ptr(),
-                                          self.ws.data_ptr(), self.ws_bytes, stream))
+        with self._on_device():
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(self.lib.sbce_ls_start(C.byref(cfg), C.byref(io), theta0.data_ptr(), status.data_ptr(),
+                                              self.ws.data_ptr(), self.ws_bytes, stream))
         return theta0, status
 
     def accumulate(self, res: "Result", Xd, acc_nmse, acc_ser=None):
@@ -372,12 +384,20 @@ class DeviceSession:
         trials, valid count, flagged count), acc_ser (3 float64: symbol errors, symbols, sum of as-coded SER)."""
         torch, p = self.torch, self.prob
         B = int(res.theta.shape[0])
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(self.lib.sbce_accumulate_nmse(res.nmse.data_ptr(), res.status.data_ptr(), B, acc_nmse.data_ptr(), stream))
-        if acc_ser is not None and res.kstar is not None and p.n_tx * int(math.log2(p.M)) <= 30:
-            cfg = p.cfg(B)
-            _lib.check(self.lib.sbce_accumulate_ser(C.byref(cfg), res.kstar.data_ptr(), Xd.data_ptr(), B,
-                                                    acc_ser.data_ptr(), stream))
+        if res.nmse is None:
+            raise ValueError("accumulate() needs Result.nmse: run(..., h_true=...) computes it")
+        # joint decisions exist in the exhaustive and detector modes only (PM modes report kstar = -1)
+        ser_ok = (acc_ser is not None and res.kstar is not None and p.mode in ("soft", "hard", "zf", "mmse")
+                  and p.n_tx * int(math.log2(p.M)) <= 30)
+        with self._on_device():
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.sbce_accumulate_nmse(res.nmse.data_ptr(),
+                                                     None if res.status is None else res.status.data_ptr(), B,
+                                                     acc_nmse.data_ptr(), stream))
+            if ser_ok:
+                cfg = p.cfg(B)
+                _lib.check(self.lib.sbce_accumulate_ser(C.byref(cfg), res.kstar.data_ptr(), Xd.data_ptr(), B,
+                                                        acc_ser.data_ptr(), stream))
 
 
 def fp64_peak_tflops():
