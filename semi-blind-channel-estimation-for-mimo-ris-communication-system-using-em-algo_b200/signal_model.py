@@ -154,9 +154,12 @@ def noisy_blocks(PsiP, PsiD, Xp, Xd, h, varn, rs, legacy=True):
     return Yp, Yd
 
 
-def generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn, B, seed=0, legacy=True, order="pm", variant="pm") -> TrialBatch:
+def generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn, B, seed=0, legacy=True, order="pm", variant="pm",
+                   ls="pinv") -> TrialBatch:
     """B independent trials; trial b uses seed + b when legacy (disjoint, reproducible
-    per trial regardless of how the batch is sharded)."""
+    per trial regardless of how the batch is sharded).  `ls` (non-legacy only): "pinv" is the reference's
+    LS start (PM.py:147); "normal" solves the pilot normal equations instead -- the same vector to rounding
+    when W_p has full column rank (T_p >= L), at O(L^3) instead of an SVD per trial (long channels)."""
     L = (N + 1) * n_tx
     varn_arr = np.broadcast_to(np.asarray(varn, dtype=np.float64), (B,)).copy()
     out = TrialBatch(h=np.empty((B, L, n_rx), np.complex128), Xd=np.empty((B, T_d, n_tx), np.complex128),
@@ -197,7 +200,13 @@ def generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn, B, seed=0, legacy=True, ord
     vn = varn_arr[:, None, None]
     out.Yp[:] = Wp @ out.h + cn((B, T_p, n_rx), 1.0) * np.sqrt(vn)
     out.Yd[:] = Wd @ out.h + cn((B, T_d, n_rx), 1.0) * np.sqrt(vn)
-    out.theta0[:] = np.linalg.pinv(Wp) @ out.Yp
+    if ls == "normal":
+        if T_p < L:
+            raise ValueError("ls='normal' needs T_p >= L (full column rank pilot block)")
+        WpH = Wp.conj().transpose(0, 2, 1)
+        out.theta0[:] = np.linalg.solve(WpH @ Wp, WpH @ out.Yp)
+    else:
+        out.theta0[:] = np.linalg.pinv(Wp) @ out.Yp
     return out
 
 
