@@ -10,7 +10,7 @@ What is measured
   (A) `Proposed_method_NMSEvsTp.py:43-69` em at its shipped size (N=32, 2x2, QPSK, T_p=40, T_d=50,
       10 iterations), complete: one trial, single Python thread.
   (B) the same function at the north-star channel size (N=64, 4x4 -> D = 1040 unknowns, T_p = 320) on a
-      SLICE: T_d = 2 data symbols and QPSK (K = 256 joint hypotheses) instead of T_d = 256 and 16-QAM
+      SLICE: T_d <= 5 data symbols and QPSK (K = 256 joint hypotheses) instead of T_d = 256 and 16-QAM
       (K = 65536), one iteration.  The function's cost per (symbol, hypothesis) pair does not depend on M
       or T_d (two np.kron chains, one (D x n_rx)(n_rx x D) product and a D x D accumulation per pair,
       :55-62), so the full workload is  itera * [ T_d * K * c_pair + T_p * c_pilot + c_solve ]  with the
@@ -67,19 +67,20 @@ def main():
                                 trials_per_s=1.0 / tA, kind="measured, complete")
     # (B) north-star channel size, slices that separate the three cost terms
     N, n_tx, n_rx = 64, 4, 4
-    t_11 = time_em(N, n_tx, n_rx, 4, 1, 1, 1)     # T_p = 1,  T_d = 1: K pairs + 1 pilot + solve
-    t_12 = time_em(N, n_tx, n_rx, 4, 1, 2, 1)     # T_p = 1,  T_d = 2
-    t_91 = time_em(N, n_tx, n_rx, 4, 9, 1, 1)     # T_p = 9,  T_d = 1
+    time_em(N, n_tx, n_rx, 4, 1, 1, 1)                                        # warm-up (imports, BLAS threads)
+    t_11 = min(time_em(N, n_tx, n_rx, 4, 1, 1, 1) for _ in range(2))          # T_p = 1,  T_d = 1: K pairs + 1 pilot + solve
+    t_15 = time_em(N, n_tx, n_rx, 4, 1, 5, 1)                                 # T_p = 1,  T_d = 5
+    t_41 = time_em(N, n_tx, n_rx, 4, 41, 1, 1)                                # T_p = 41, T_d = 1
     K_slice = 4 ** n_tx
-    c_pair = (t_12 - t_11) / K_slice              # seconds per (symbol, hypothesis) pair, both loops
-    c_pilot = (t_91 - t_11) / 8.0                 # seconds per pilot symbol
+    c_pair = (t_15 - t_11) / (4.0 * K_slice)      # seconds per (symbol, hypothesis) pair, both loops
+    c_pilot = max(0.0, (t_41 - t_11) / 40.0)      # seconds per pilot symbol
     c_solve = max(0.0, t_11 - K_slice * c_pair - c_pilot)
     T_p, T_d, K, itera = 320, 256, 16 ** n_tx, 10
     per_iter = T_d * K * c_pair + T_p * c_pilot + c_solve
     out["north_star_extrapolated"] = dict(
         N=N, n_tx=n_tx, n_rx=n_rx, M=16, T_p=T_p, T_d=T_d, itera=itera,
-        slice="T_d in {1,2}, T_p in {1,9}, QPSK (K=256), 1 iteration each",
-        slice_seconds=dict(tp1_td1=t_11, tp1_td2=t_12, tp9_td1=t_91),
+        slice="T_d in {1,5}, T_p in {1,41}, QPSK (K=256), 1 iteration each",
+        slice_seconds=dict(tp1_td1=t_11, tp1_td5=t_15, tp41_td1=t_41),
         c_pair_s=c_pair, c_pilot_s=c_pilot, c_solve_s=c_solve,
         seconds_per_iteration=per_iter, seconds_per_trial=itera * per_iter,
         trials_per_s=1.0 / (itera * per_iter), kind="extrapolated from the slice")

@@ -24,6 +24,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "tensor.cuh"
 
 namespace sbce {
 
@@ -32,23 +33,6 @@ namespace sbce {
 // ---------------------------------------------------------------------------
 constexpr int GR_THREADS = 256;
 constexpr int GR_TC = 16;  // symbols per shared-memory chunk (default; shrunk at launch for very long psi rows)
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
-// FP64 tensor-path MMA (SASS: 4 x DMMA.8x8x4).  Fragment layout verified by tools/microbench/dmma_layout.cu.
-__device__ __forceinline__ void dmma16x8x8(double (&c)[4], const double (&a)[4], double b0, double b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
-        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b0), "d"(b1));
-}
-
 
 constexpr int RH_MAXR = 8;
 
@@ -287,28 +271,6 @@ __device__ __forceinline__ int gram_bcol_offset(int col) {
 // staging: each waits on the stage's `full` mbarrier, runs its DMMAs and arrives on `empty` on its own
 // -- no __syncthreads in the loop, so a slow warp no longer stalls the other seven.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 constexpr int GT_TC = 16;        // symbols per stage
 constexpr int GT_STAGES = 4;     // ring depth
 constexpr int GT_THREADS = GR_THREADS;        // 8 DMMA warps; warp 0's elected lane also drives the TMA ring
@@ -696,337 +658,6 @@ cudaError_t launch_normal_equations(const Dims& d, int nb, const double* Psi, in
         case 8: return run_gram_wide<8>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
         default: return cudaErrorInvalidValue;
     }
-}
-
-// ---------------------------------------------------------------------------
-// Blocked Cholesky of the augmented trapezoid + back substitution
-// ---------------------------------------------------------------------------
-constexpr int CH_NB = 16;            // panel width
-constexpr int CH_DS = CH_NB + 1;     // row stride (complex) of the shared 16x16 blocks
-
-
-// k_chol2: LEFT-looking blocked complex Cholesky (panel width 16) on the FP64 tensor path (mma.sync
-// m16n8k8.f64, SASS DMMA) with LOOK-AHEAD.  Iteration k works on the 16-row tiles below the diagonal block of
-// panel k, and every tile is taken through TWO steps by the warp that claimed it:
-//   A. X = S W_k^H            (triangular solve of panel k as a GEMM against the inverse of the diagonal
-//                              block, 16 DMMA quads), then
-//   B. S' = A - C[rows, 0:g0] C[g0:g0+16, 0:g0]^H   (update for panel k+1 against ALL previous columns,
-//      operand fragments double-buffered in registers so the loads of step q+1 are in flight during the
-//      DMMAs of step q).
-// Warp 0 takes tile 0 -- the next diagonal block row -- first, publishes "block row ready" through a
-// shared flag (the other warps need its freshly solved columns as the B operand of step B), then factors
-// the next diagonal block and its inverse W_{k+1} into the other shared buffer while the other warps chew
-// through the remaining tiles: one CTA barrier per panel.  The trailing matrix is never touched; the B^H
-// rows carried under the matrix come out as (C^-1 B)^H, i.e. the forward substitution is free.  (Its
-// two-barrier predecessor with a shared-memory diagonal factor is documented in profiles/r01h-r01j.)
-// ---------------------------------------------------------------------------
-
-// Diagonal block of the look-ahead kernel, register resident.  Profiling (profiles/r01i) showed the
-// shared-memory version above on warp 0's critical path for 43 % of the kernel: ~55k cycles per panel of
-// LDS -> DFMA -> STS round trips that the compiler cannot overlap (possible aliasing), a DSQRT + DDIV per
-// column and a DDIV per row of the inverse.  Here lane r (and its mirror r + 16) keeps row r of the block in
-// registers; column c is a left-looking dot product against row c, fetched with width-16 shuffles; the
-// pivot is broadcast, inverted once with rsqrt (no division anywhere); the inverse W = L^-1 is built column
-// per lane from broadcast reads of L in shared memory.  W's strict lower part is parked in the unused
-// strict UPPER triangle of the diagonal block in global memory (A[k0+j][k0+i] = W[i][j], i > j) so that
-// the back substitution can apply W^H instead of running a serial triangular solve.
-__device__ __forceinline__ void chol_diag_factor_reg(const Dims& d, cplx* A, int ld, int k0, int nb, cplx* sD, cplx* sW,
-                                                     int lane, double& maxpiv, int* s_bad) {
-    const unsigned full = 0xffffffffu;
-    const int r = lane & 15;
-    cplx a[CH_NB];
-    {
-        const cplx* rowp = A + (size_t)(k0 + min(r, nb - 1)) * ld + k0;
-#pragma unroll
-        for (int c = 0; c < CH_NB; ++c) a[c] = (r < nb && c <= r && c < nb) ? rowp[c] : mk(0.0, 0.0);
-    }
-    double invs[CH_NB];
-#pragma unroll
-    for (int c = 0; c < CH_NB; ++c) {
-        cplx s = a[c];
-#pragma unroll
-        for (int q = 0; q < c; ++q) {
-            const cplx lcq = mk(__shfl_sync(full, a[q].x, c, 16), __shfl_sync(full, a[q].y, c, 16));
-            cfmsc(s, a[q], lcq);   // s -= L[r][q] conj(L[c][q])
-        }
-        double piv = __shfl_sync(full, s.x, c, 16);
-        const bool live = c < nb;
-        if (live) {
-            // numerically singular: non-positive, or below 1e-13 of the largest pivot so far; identity padding exempt
-            if (!(piv > ((k0 + c < d.L) ? 1e-13 * maxpiv : 0.0))) {
-                if (lane == 0) *s_bad = 1;
-                piv = 1.0;
-            }
-            maxpiv = fmax(maxpiv, piv);
-        } else {
-            piv = 1.0;
-        }
-        const double inv = rsqrt(piv);
-        invs[c] = live ? inv : 0.0;
-        a[c] = (!live || r < c) ? mk(0.0, 0.0) : (r == c ? mk(piv * inv, 0.0) : cscale(s, inv));
-    }
-    if (lane < CH_NB) {
-#pragma unroll
-        for (int c = 0; c < CH_NB; ++c) sD[r * CH_DS + c] = a[c];
-    }
-    __syncwarp();
-    // W = L^-1, lane = column j:  W[i][j] = -inv_i sum_{q<i} L[i][q] W[q][j]  (W[q][j] = 0 for q < j)
-    cplx w[CH_NB];
-#pragma unroll
-    for (int i = 0; i < CH_NB; ++i) {
-        cplx acc0 = mk(0.0, 0.0), acc1 = mk(0.0, 0.0);
-#pragma unroll
-        for (int q = 0; q < i; ++q) {
-            if (q & 1) cfma(acc1, sD[i * CH_DS + q], w[q]); else cfma(acc0, sD[i * CH_DS + q], w[q]);
-        }
-        w[i] = (i == r) ? mk(invs[i], 0.0) : mk(-invs[i] * (acc0.x + acc1.x), -invs[i] * (acc0.y + acc1.y));
-    }
-    if (lane < CH_NB) {
-#pragma unroll
-        for (int i = 0; i < CH_NB; ++i) sW[i * CH_DS + r] = w[i];
-        if (r < nb) {   // row k0 + r of the block: L up to the diagonal, then W^T
-            cplx* rowp = A + (size_t)(k0 + r) * ld + k0;
-#pragma unroll
-            for (int c = 0; c < CH_NB; ++c)
-                if (c < nb) rowp[c] = (c <= r) ? sD[r * CH_DS + c] : w[c];
-        }
-    }
-    __syncwarp();
-}
-
-template <int CH_THREADS, int CH_MINB>
-__global__ void __launch_bounds__(CH_THREADS, CH_MINB) k_chol2(Dims d, cplx* __restrict__ Gall,
-                                                               cplx* __restrict__ theta,
-                                                               const int32_t* __restrict__ active,
-                                                               int32_t* __restrict__ stat, cplx* th_global) {
-    extern __shared__ double2 csm[];
-    const int b = blockIdx.x;
-    if (active != nullptr && active[b] == 0) return;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, tig = lane & 3;
-    const int Lp = d.Lp, Ltot = d.Ltot, ld = d.Lp;
-    cplx* A = Gall + (size_t)b * Ltot * Lp;
-
-    cplx* sD = csm;                       // [16][17] diagonal block being factored (later: back substitution)
-    cplx* sWb = sD + CH_NB * CH_DS;       // [2][16][17] inverse of the diagonal block, double buffered
-    cplx* th = th_global ? th_global + (size_t)b * d.Lp * d.n_rx : sWb + 2 * CH_NB * CH_DS;
-    __shared__ int s_bad, s_next[2];
-    __shared__ volatile int s_ready;      // panels whose diagonal block ROW is final (written by warp 0)
-    if (tid == 0) { s_bad = 0; s_next[0] = 1; s_next[1] = 1; s_ready = 0; }
-    double maxpiv = 0.0;
-    const int npan = (Lp + CH_NB - 1) / CH_NB;
-    if (warp == 0) chol_diag_factor_reg(d, A, ld, 0, min(CH_NB, Lp), sD, sWb, lane, maxpiv, &s_bad);
-    __syncthreads();
-
-    auto claim = [&](int* counter) {
-        int v = 0;
-        if (lane == 0) v = atomicAdd(counter, 1);
-        return __shfl_sync(0xffffffffu, v, 0);
-    };
-
-    for (int k = 0; k < npan; ++k) {
-        const int k0 = k * CH_NB;
-        const int nb = min(CH_NB, Lp - k0);
-        const int g0 = k0 + nb;                               // first row below the diagonal block = next panel
-        const int nbn = (k + 1 < npan) ? min(CH_NB, Lp - g0) : 0;
-        const int ntile = (Ltot - g0 + 15) >> 4;
-        const cplx* sW = sWb + (k & 1) * CH_NB * CH_DS;
-        if (tid == 0) s_next[(k + 1) & 1] = 1;                // next iteration's counter (idle during this one)
-
-        auto tile = [&](int t) {
-            const int r0 = g0 + (t << 4);
-            const int ra = min(r0 + g, Ltot - 1), rb8 = min(r0 + g + 8, Ltot - 1);
-            double cr[2][4], ci[2][4];
-            // ---- step A: X = S W^H on columns k0 .. k0+nb-1
-            {
-                const cplx* pa0 = A + (size_t)ra * ld + k0 + tig;
-                const cplx* pa1 = A + (size_t)rb8 * ld + k0 + tig;
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { cr[j][e] = 0.0; ci[j][e] = 0.0; }
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const int q0 = 8 * kk + tig;
-                    cplx a0 = mk(0, 0), a1 = mk(0, 0), a2 = mk(0, 0), a3 = mk(0, 0);
-                    if (q0 < nb) { a0 = pa0[8 * kk]; a1 = pa1[8 * kk]; }
-                    if (q0 + 4 < nb) { a2 = pa0[8 * kk + 4]; a3 = pa1[8 * kk + 4]; }
-                    const double ar[4] = {a0.x, a1.x, a2.x, a3.x};
-                    const double ai[4] = {a0.y, a1.y, a2.y, a3.y};
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const cplx w0 = sW[(8 * j + g) * CH_DS + 8 * kk + tig];
-                        const cplx w1 = sW[(8 * j + g) * CH_DS + 8 * kk + tig + 4];
-                        dmma16x8x8(cr[j], ar, w0.x, w1.x);
-                        dmma16x8x8(cr[j], ai, w0.y, w1.y);
-                        dmma16x8x8(ci[j], ai, w0.x, w1.x);
-                        dmma16x8x8(ci[j], ar, -w0.y, -w1.y);
-                    }
-                }
-                __syncwarp();  // all lanes have read S before anyone overwrites it
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int row = r0 + g + 8 * h;
-                        const int c = 8 * j + 2 * tig;
-                        if (row < Ltot && c < nb) {
-                            cplx* p2 = A + (size_t)row * ld + k0 + c;
-                            p2[0] = mk(cr[j][2 * h], ci[j][2 * h]);
-                            p2[1] = mk(cr[j][2 * h + 1], ci[j][2 * h + 1]);
-                        }
-                    }
-            }
-            if (nbn == 0) return;
-            __threadfence_block();
-            __syncwarp();
-            if (t == 0) {
-                if (lane == 0) s_ready = k + 1;               // block row g0.. is final in columns < g0
-            } else {
-                while (s_ready < k + 1) __nanosleep(32);
-                __threadfence_block();
-            }
-            // ---- step B: S' = A[rows, g0:g0+nbn] - C[rows, 0:g0] C[g0:g0+16, 0:g0]^H
-            {
-                const cplx* pa0 = A + (size_t)ra * ld + tig;
-                const cplx* pa1 = A + (size_t)rb8 * ld + tig;
-                const cplx* pb0 = A + (size_t)min(g0 + g, Ltot - 1) * ld + tig;
-                const cplx* pb1 = A + (size_t)min(g0 + 8 + g, Ltot - 1) * ld + tig;
-                // the block to be updated is only needed at the very end: start fetching it now
-                if (tig == 0) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)ra * ld + g0));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)ra * ld + g0 + 8));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)rb8 * ld + g0));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)rb8 * ld + g0 + 8));
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { cr[j][e] = 0.0; ci[j][e] = 0.0; }
-                cplx fa[4], fb[4];
-                fa[0] = pa0[0]; fa[1] = pa1[0]; fa[2] = pa0[4]; fa[3] = pa1[4];
-                fb[0] = pb0[0]; fb[1] = pb0[4]; fb[2] = pb1[0]; fb[3] = pb1[4];
-#pragma unroll 1
-                for (int q0 = 0; q0 < g0; q0 += 8) {
-                    cplx na[4], nbq[4];
-                    const int qn = (q0 + 8 < g0) ? q0 + 8 : q0;   // last step reloads itself (harmless, L1 hit)
-                    na[0] = pa0[qn]; na[1] = pa1[qn]; na[2] = pa0[qn + 4]; na[3] = pa1[qn + 4];
-                    nbq[0] = pb0[qn]; nbq[1] = pb0[qn + 4]; nbq[2] = pb1[qn]; nbq[3] = pb1[qn + 4];
-                    const double ar[4] = {fa[0].x, fa[1].x, fa[2].x, fa[3].x};
-                    const double ai[4] = {fa[0].y, fa[1].y, fa[2].y, fa[3].y};
-                    // sum_q a conj(b):  re += ar br + ai bi ;  im += ai br - ar bi
-                    dmma16x8x8(cr[0], ar, fb[0].x, fb[1].x);
-                    dmma16x8x8(cr[0], ai, fb[0].y, fb[1].y);
-                    dmma16x8x8(ci[0], ai, fb[0].x, fb[1].x);
-                    dmma16x8x8(ci[0], ar, -fb[0].y, -fb[1].y);
-                    dmma16x8x8(cr[1], ar, fb[2].x, fb[3].x);
-                    dmma16x8x8(cr[1], ai, fb[2].y, fb[3].y);
-                    dmma16x8x8(ci[1], ai, fb[2].x, fb[3].x);
-                    dmma16x8x8(ci[1], ar, -fb[2].y, -fb[3].y);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { fa[e] = na[e]; fb[e] = nbq[e]; }
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int row = r0 + g + 8 * h;
-                        const int c = 8 * j + 2 * tig;
-                        if (row < Ltot && c < nbn) {
-                            cplx* p2 = A + (size_t)row * ld + g0 + c;
-                            const cplx v0 = p2[0], v1 = p2[1];
-                            p2[0] = mk(v0.x - cr[j][2 * h], v0.y - ci[j][2 * h]);
-                            p2[1] = mk(v1.x - cr[j][2 * h + 1], v1.y - ci[j][2 * h + 1]);
-                        }
-                    }
-            }
-        };
-
-        if (warp == 0) {
-            tile(0);
-            if (nbn > 0) {
-                __threadfence_block();
-                __syncwarp();
-                chol_diag_factor_reg(d, A, ld, g0, nbn, sD, sWb + ((k + 1) & 1) * CH_NB * CH_DS, lane, maxpiv, &s_bad);
-            }
-        }
-        for (int t = claim(&s_next[k & 1]); t < ntile; t = claim(&s_next[k & 1])) tile(t);
-        __syncthreads();   // W_{k+1} is ready, every tile of this iteration is written
-    }
-    if (tid == 0 && s_bad && stat) atomicOr(&stat[b], SBCE_ST_NOT_PD);
-
-    // ---- back substitution  C^H theta = z,  z[l][r] = conj(A[Lp + r][l])  (as in k_chol)
-    const int nrx = d.n_rx;
-    for (int e = tid; e < Lp * nrx; e += CH_THREADS) {
-        const int l = e / nrx, r = e % nrx;
-        th[e] = cconj(A[(size_t)(Lp + r) * ld + l]);
-    }
-    for (int k0 = ((Lp - 1) / CH_NB) * CH_NB; k0 >= 0; k0 -= CH_NB) {
-        const int nb = min(CH_NB, Lp - k0);
-        __syncthreads();  // th updates of the previous block are complete
-        // D^H x = rhs  <=>  x = W^H rhs with W = D^-1 parked in the block's strict upper triangle:
-        // x[c] = rhs[c] / D[c][c] + sum_{q>c} conj(W[q][c]) rhs[q], one thread per (c, right-hand side)
-        const bool act = tid < nb * nrx;
-        const int bc = act ? tid / nrx : 0, br = act ? tid % nrx : 0;
-        cplx xv = mk(0.0, 0.0);
-        if (act) {
-            const cplx* wrow = A + (size_t)(k0 + bc) * ld + k0;
-            xv = cscale(th[(k0 + bc) * nrx + br], 1.0 / wrow[bc].x);
-            for (int q = bc + 1; q < nb; ++q) cfmac(xv, th[(k0 + q) * nrx + br], wrow[q]);
-        }
-        __syncthreads();
-        if (act) th[(k0 + bc) * nrx + br] = xv;
-        __syncthreads();
-        // th[c][:] -= sum_q conj(C[k0+q][c]) x[q][:]   for all c < k0
-        for (int c = tid; c < k0; c += CH_THREADS) {
-            cplx cq[CH_NB];
-#pragma unroll
-            for (int q = 0; q < CH_NB; ++q) cq[q] = (q < nb) ? A[(size_t)(k0 + q) * ld + c] : mk(0.0, 0.0);
-            for (int r = 0; r < nrx; ++r) {
-                cplx v = th[c * nrx + r];
-#pragma unroll
-                for (int q = 0; q < CH_NB; ++q)
-                    if (q < nb) cfmsc(v, th[(k0 + q) * nrx + r], cq[q]);
-                th[c * nrx + r] = v;
-            }
-        }
-    }
-    __syncthreads();
-    cplx* out = theta + (size_t)b * d.L * nrx;
-    bool bad = false;
-    for (int e = tid; e < d.L * nrx; e += CH_THREADS) {
-        const cplx v = th[e];
-        out[e] = v;
-        if (!isfinite(v.x) || !isfinite(v.y)) bad = true;
-    }
-    if (bad && stat) atomicOr(&stat[b], SBCE_ST_NONFINITE);
-}
-
-template <int T, int MB>
-static cudaError_t run_chol2(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
-                             size_t smem, double* thg, cudaStream_t s) {
-    static SmemOptIn optin;
-    cudaError_t e = opt_in_smem(optin, (const void*)k_chol2<T, MB>, smem);
-    if (e != cudaSuccess) return e;
-    k_chol2<T, MB><<<nb, T, smem, s>>>(d, (cplx*)G, (cplx*)theta, active, stat, (cplx*)thg);
-    count_launch();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
-                              double* th_scratch, cudaStream_t s) {
-    size_t thsz = (size_t)d.Lp * d.n_rx;
-    size_t smem = sizeof(cplx) * (3 * CH_NB * CH_DS + thsz);
-    double* thg = nullptr;
-    if (smem > 48 * 1024) {   // keep four trials resident per SM: the solution vector moves to global scratch
-        if (!th_scratch) return cudaErrorInvalidValue;
-        thg = th_scratch;
-        smem = sizeof(cplx) * (3 * CH_NB * CH_DS);
-    }
-    // CTA shapes measured on B200 (N=64, 4x4: L=260, 592 trials) for the look-ahead kernel:
-    // 128 threads x 4 CTAs/SM 0.98 ms, 96 x 5 1.27 ms, 256 x 2 1.57 ms, 160 x 3 1.45 ms, 128 x 5 (96 registers)
-    // 1.11 ms -- latency bound, more resident trials per SM win even though their factors no longer fit in L2.
-    return run_chol2<128, 4>(d, nb, G, theta, active, stat, smem, thg, s);
 }
 
 }  // namespace sbce

@@ -11,7 +11,7 @@ import pytest
 import sbce
 from conftest import load_golden
 from oracle import em_numpy as orc
-from oracle.make_config_golden import input_digest
+from oracle.make_config_golden import check_inputs
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -51,7 +51,7 @@ def test_config_fixture_inputs_regenerate_bit_identically(name, key):
     w = sbce.workloads.WORKLOADS[key]
     B, trials = int(meta["B"]), [int(t) for t in meta["trials"]]
     tb = sbce.workloads.make_batch(w, B)
-    assert input_digest(tb, trials) == str(meta["digest"])
+    check_inputs(tb, trials, meta["digest"], g["probes"])
     for i, b in enumerate(trials):
         assert abs(orc.nmse(g["theta_ref"][i], tb.h[b]) - g["nmse_ref"][i]) <= 1e-12 * g["nmse_ref"][i]
     assert g["theta_ref"].shape == (len(trials), w.L, w.n_rx)
