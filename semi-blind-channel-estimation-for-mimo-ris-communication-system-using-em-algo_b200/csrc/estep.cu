@@ -32,6 +32,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "tensor.cuh"
 
 namespace sbce {
 
@@ -63,44 +64,13 @@ cudaError_t launch_pilot_stats(const Dims& d, int nb, const double* Xp, double* 
 // ---------------------------------------------------------------------------
 // 1. effective channel + Householder QR, one lane per symbol
 // ---------------------------------------------------------------------------
+// Per-lane tail shared by the effective-channel kernels: A = Heff_t (rows >= NRX zero), then
+// y' = y - Heff o_t (superimposed pilots), Householder QR of [A | y] in registers, record store.
 template <int NTX, int NRX>
-__global__ void __launch_bounds__(128) k_heff_qr(Dims d, const cplx* __restrict__ Yd, const cplx* __restrict__ PsiD,
-                                                 const cplx* __restrict__ theta, const int32_t* __restrict__ active,
-                                                 const cplx* __restrict__ Xoff, double* __restrict__ qr, int use_smem) {
+__device__ __forceinline__ void heff_qr_finish(const Dims& d, int b, int t, cplx (&A)[cmax(NTX, NRX)][NTX],
+                                               const cplx* __restrict__ Yd, const cplx* __restrict__ Xoff,
+                                               double* __restrict__ qr) {
     constexpr int NR = cmax(NTX, NRX);
-    extern __shared__ double2 heff_smem[];
-    const int b = blockIdx.y;
-    if (active != nullptr && active[b] == 0) return;
-    // theta of the trial is read by every lane at warp-uniform addresses, 16 values per RIS index: staged in
-    // shared memory once per CTA (coalesced) the inner loop issues LDS broadcasts instead of global loads
-    // (the global-load queue was the kernel's top stall, profiles/r01m); use_smem = 0: theta too long
-    const cplx* th = theta + (size_t)b * d.L * NRX;
-    if (use_smem) {
-        for (int e = threadIdx.x; e < d.L * NRX; e += blockDim.x) heff_smem[e] = th[e];
-        __syncthreads();
-        th = heff_smem;
-    }
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= d.T_d) return;
-
-    const cplx* psi = PsiD + ((size_t)(d.psi_shared ? 0 : b) * d.T_d + t) * d.N1;
-
-    cplx A[NR][NTX];
-#pragma unroll
-    for (int r = 0; r < NR; ++r)
-#pragma unroll
-        for (int j = 0; j < NTX; ++j) A[r][j] = mk(0.0, 0.0);
-
-    // Heff[r][j] = sum_n' psi~[t][n'] Theta[n'*n_tx + j][r]; theta reads are warp-uniform (broadcast)
-#pragma unroll 4
-    for (int n = 0; n < d.N1; ++n) {
-        const cplx p = psi[n];
-        const cplx* row = th + (size_t)n * NTX * NRX;
-#pragma unroll
-        for (int j = 0; j < NTX; ++j)
-#pragma unroll
-            for (int r = 0; r < NRX; ++r) cfma(A[r][j], p, row[j * NRX + r]);
-    }
     cplx y[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) y[r] = (r < NRX) ? Yd[((size_t)b * d.T_d + t) * NRX + r] : mk(0.0, 0.0);
@@ -181,6 +151,146 @@ __global__ void __launch_bounds__(128) k_heff_qr(Dims d, const cplx* __restrict_
     for (int i = NTX; i < NR; ++i) c0 += cnorm2(y[i]);
     rec[o++] = c0;
     rec[o++] = 0.0;
+}
+
+template <int NTX, int NRX>
+__global__ void __launch_bounds__(128) k_heff_qr(Dims d, const cplx* __restrict__ Yd, const cplx* __restrict__ PsiD,
+                                                 const cplx* __restrict__ theta, const int32_t* __restrict__ active,
+                                                 const cplx* __restrict__ Xoff, double* __restrict__ qr, int use_smem) {
+    constexpr int NR = cmax(NTX, NRX);
+    extern __shared__ double2 heff_smem[];
+    const int b = blockIdx.y;
+    if (active != nullptr && active[b] == 0) return;
+    // theta of the trial is read by every lane at warp-uniform addresses, 16 values per RIS index: staged in
+    // shared memory once per CTA (coalesced) the inner loop issues LDS broadcasts instead of global loads
+    // (the global-load queue was the kernel's top stall, profiles/r01m); use_smem = 0: theta too long
+    const cplx* th = theta + (size_t)b * d.L * NRX;
+    if (use_smem) {
+        for (int e = threadIdx.x; e < d.L * NRX; e += blockDim.x) heff_smem[e] = th[e];
+        __syncthreads();
+        th = heff_smem;
+    }
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.T_d) return;
+
+    const cplx* psi = PsiD + ((size_t)(d.psi_shared ? 0 : b) * d.T_d + t) * d.N1;
+
+    cplx A[NR][NTX];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int j = 0; j < NTX; ++j) A[r][j] = mk(0.0, 0.0);
+
+    // Heff[r][j] = sum_n' psi~[t][n'] Theta[n'*n_tx + j][r]; theta reads are warp-uniform (broadcast)
+#pragma unroll 4
+    for (int n = 0; n < d.N1; ++n) {
+        const cplx p = psi[n];
+        const cplx* row = th + (size_t)n * NTX * NRX;
+#pragma unroll
+        for (int j = 0; j < NTX; ++j)
+#pragma unroll
+            for (int r = 0; r < NRX; ++r) cfma(A[r][j], p, row[j * NRX + r]);
+    }
+    heff_qr_finish<NTX, NRX>(d, b, t, A, Yd, Xoff, qr);
+}
+
+// ---------------------------------------------------------------------------
+// 1a. the same on the FP64 tensor path.  Heff = Psi_d (T_d x N+1) . Theta (N+1 x n_tx n_rx) is a dense complex
+// GEMM per trial (the RIS contraction, Proposed_method_NMSEvsTp.py:56 without the Kronecker products); the
+// per-lane kernel above streams each lane's psi row with stride-(N+1) 16-byte loads (17 % of HBM peak, the
+// load queue is its top stall, profiles/r01m).  Here a warp owns 32 symbols = two 16-row MMA tiles: A
+// fragments (psi) are 128-byte row segments per 8-column step straight from global memory, B fragments
+// (Theta, shared by the whole CTA) come from a padded shared-memory copy; the 2 x NT x 4 accumulators are
+// transposed through shared memory so that lane t ends up with Heff_t in registers and runs the same
+// Householder tail.
+// ---------------------------------------------------------------------------
+template <int NTX, int NRX>
+__global__ void __launch_bounds__(128, 4) k_heff_qr_mma(Dims d, const cplx* __restrict__ Yd,
+                                                        const cplx* __restrict__ PsiD, const cplx* __restrict__ theta,
+                                                        const int32_t* __restrict__ active,
+                                                        const cplx* __restrict__ Xoff, double* __restrict__ qr) {
+    constexpr int NR = cmax(NTX, NRX);
+    constexpr int NC = NTX * NRX;          // complex columns of the GEMM: (j, r) -> j * NRX + r
+    constexpr int NT = (NC + 7) / 8;       // 8-column MMA tiles
+    constexpr int TS = NT * 8 + 2;         // row stride of the staged Theta: fragment loads are conflict-free
+    constexpr int HS = NC + 1;             // row stride of the transposed result
+    extern __shared__ double2 heff_smem[];
+    const int b = blockIdx.y;
+    if (active != nullptr && active[b] == 0) return;
+    const int N1 = d.N1, KP = (N1 + 7) & ~7;
+    cplx* sTh = heff_smem;                 // [KP][TS], rows >= N1 and columns >= NC zero
+    cplx* sH = sTh + KP * TS;              // [4 warps][32][HS]
+    {
+        const cplx* th = theta + (size_t)b * d.L * NRX;
+        for (int e = threadIdx.x; e < KP * TS; e += blockDim.x) {
+            const int n = e / TS, c = e % TS;
+            sTh[e] = (n < N1 && c < NC) ? th[n * NC + c] : mk(0.0, 0.0);
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    const int t0 = blockIdx.x * 128 + warp * 32;
+    if (t0 >= d.T_d) return;
+    const cplx* psi_b = PsiD + (size_t)(d.psi_shared ? 0 : b) * d.T_d * N1;
+    const cplx* prow[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) prow[mt][h] = psi_b + (size_t)min(t0 + mt * 16 + g + 8 * h, d.T_d - 1) * N1;
+    double cr[2][NT][4], ci[2][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { cr[mt][nt][e] = 0.0; ci[mt][nt][e] = 0.0; }
+#pragma unroll 2
+    for (int k0 = 0; k0 < KP; k0 += 8) {
+        const int ka = k0 + tig, kb = ka + 4;
+        const bool va = ka < N1, vb = kb < N1;
+        double ar[2][4], ai[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            // A fragment order: (row g, k lo), (row g+8, k lo), (row g, k hi), (row g+8, k hi)
+            const cplx a0 = va ? prow[mt][0][ka] : mk(0.0, 0.0), a1 = va ? prow[mt][1][ka] : mk(0.0, 0.0);
+            const cplx a2 = vb ? prow[mt][0][kb] : mk(0.0, 0.0), a3 = vb ? prow[mt][1][kb] : mk(0.0, 0.0);
+            ar[mt][0] = a0.x; ar[mt][1] = a1.x; ar[mt][2] = a2.x; ar[mt][3] = a3.x;
+            ai[mt][0] = a0.y; ai[mt][1] = a1.y; ai[mt][2] = a2.y; ai[mt][3] = a3.y;
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const cplx b0 = sTh[ka * TS + 8 * nt + g], b1 = sTh[kb * TS + 8 * nt + g];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                // (ar + i ai)(br + i bi): re += ar br - ai bi ; im += ar bi + ai br
+                dmma16x8x8(cr[mt][nt], ar[mt], b0.x, b1.x);
+                dmma16x8x8(ci[mt][nt], ar[mt], b0.y, b1.y);
+                dmma16x8x8(cr[mt][nt], ai[mt], -b0.y, -b1.y);
+                dmma16x8x8(ci[mt][nt], ai[mt], b0.x, b1.x);
+            }
+        }
+    }
+    // transpose through shared memory: accumulator (row g + 8h, columns 8 nt + 2 tig, + 1) -> H[symbol][column]
+    cplx* H = sH + (size_t)warp * 32 * HS;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int row = mt * 16 + g + 8 * h, c = 8 * nt + 2 * tig;
+                if (c < NC) H[row * HS + c] = mk(cr[mt][nt][2 * h], ci[mt][nt][2 * h]);
+                if (c + 1 < NC) H[row * HS + c + 1] = mk(cr[mt][nt][2 * h + 1], ci[mt][nt][2 * h + 1]);
+            }
+    __syncwarp();
+    const int t = t0 + lane;
+    if (t >= d.T_d) return;
+    cplx A[NR][NTX];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int j = 0; j < NTX; ++j) A[r][j] = (r < NRX) ? H[lane * HS + j * NRX + r] : mk(0.0, 0.0);
+    heff_qr_finish<NTX, NRX>(d, b, t, A, Yd, Xoff, qr);
 }
 
 // ---------------------------------------------------------------------------
@@ -367,9 +477,93 @@ __device__ __noinline__ void enum_flush(double* ws, double warp_best) {
         for (int i = lane; i < E::NACC; i += 32) ws[E::O_ACC + i] *= f;
         aref = warp_best;
     }
-    // one queue entry per lane per round; the warp reduces every statistic right away (rare path: keep
-    // the register footprint small so that it does not limit the occupancy of the scan loop)
     double* A = ws + E::O_ACC;
+    // Narrow path.  At operating SNRs the queue almost always holds ONE node (the arg-min node, whose M leaves
+    // carry the whole posterior) or two; the general path below would run all 32 lanes through ~700
+    // instructions (9 exponentials in sequence per lane) for it.  Here the warp shares one entry: the lanes of
+    // a 2*SQM group take one PAM level of the in-phase or of the quadrature component each (one exponential
+    // per lane, min / sums by xor shuffles), every lane then holds the node's closed-form leaf sums and lane i
+    // adds statistic i.
+    if (n <= 2) {
+        constexpr int LG = (SQM == 2 ? 1 : (SQM == 4 ? 2 : 3));
+        const int a = lane & (SQM - 1);
+        const bool isQ = (lane >> LG) & 1;
+        const double pq = E::pam(a);
+        for (int e = 0; e < n; ++e) {
+            const int code = q[e];
+            double base = ws[E::O_C0];
+            cplx t0;
+            {
+                cplx acc[NTX];
+#pragma unroll
+                for (int i = 0; i < NTX; ++i) acc[i] = mk(ws[E::O_YT + 2 * i], ws[E::O_YT + 2 * i + 1]);
+#pragma unroll
+                for (int s = NTX - 1; s >= 1; --s) {
+                    const int m = (code >> (E::BITS * (NTX - 1 - s))) & (M - 1);
+                    const double eI = acc[s].x - g[s * SQM + (m & (SQM - 1))];
+                    const double eQ = acc[s].y - g[s * SQM + (m >> E::HB)];
+                    base += fma(eI, eI, eQ * eQ);
+#pragma unroll
+                    for (int i = 0; i < NTX; ++i)
+                        if (i < s) acc[i] = csub(acc[i], tab[E::pair(i, s) * M + m]);
+                }
+                t0 = acc[0];
+            }
+            const double ev = (isQ ? t0.y : t0.x) - g[a];
+            const double dd = ev * ev;
+            double mn = dd;
+#pragma unroll
+            for (int o = SQM / 2; o > 0; o >>= 1) mn = fmin(mn, shfl_xor_d(mn, o));
+            const double w = exp((mn - dd) * inv_s2);
+            double s0 = w, s1 = pq * w, s2 = pq * pq * w;
+#pragma unroll
+            for (int o = SQM / 2; o > 0; o >>= 1) {
+                s0 += shfl_xor_d(s0, o);
+                s1 += shfl_xor_d(s1, o);
+                s2 += shfl_xor_d(s2, o);
+            }
+            const double o0 = shfl_xor_d(s0, SQM), o1 = shfl_xor_d(s1, SQM), o2 = shfl_xor_d(s2, SQM);
+            const double om = shfl_xor_d(mn, SQM);
+            const double EI = isQ ? o0 : s0, A1 = isQ ? o1 : s1, A2 = isQ ? o2 : s2, minI = isQ ? om : mn;
+            const double EQ = isQ ? s0 : o0, B1 = isQ ? s1 : o1, B2 = isQ ? s2 : o2, minQ = isQ ? mn : om;
+            const double W = exp((aref - (base + minI + minQ)) * inv_s2);
+            const double E0 = W * EI * EQ;
+            const cplx F0 = mk(W * A1 * EQ, -W * EI * B1);  // sum over leaves of e * conj(x_0)
+            const double Q0 = W * (A2 * EQ + EI * B2);      // sum over leaves of e * |x_0|^2
+            auto add = [&](int idx, double v) { if ((idx & 31) == lane) A[idx] += v; };
+            add(0, E0);
+            add(1, F0.x);
+            add(1 + NTX, F0.y);
+            add(1 + 2 * NTX, Q0);
+#pragma unroll
+            for (int s = 1; s < NTX; ++s) {
+                const cplx xs = E::cval((code >> (E::BITS * (NTX - 1 - s))) & (M - 1));
+                add(1 + s, E0 * xs.x);
+                add(1 + NTX + s, -E0 * xs.y);
+                add(1 + 2 * NTX + s, E0 * cnorm2(xs));
+                const cplx v = cmul(F0, xs);  // conj(x_0) x_s summed over the leaves
+                add(1 + 3 * NTX + 2 * E::pair(0, s), v.x);
+                add(1 + 3 * NTX + 2 * E::pair(0, s) + 1, v.y);
+#pragma unroll
+                for (int i = 1; i < NTX; ++i)
+                    if (i < s) {
+                        const cplx xi = E::cval((code >> (E::BITS * (NTX - 1 - i))) & (M - 1));
+                        const cplx cx = cmulc(xs, xi);  // conj(x_i) x_s
+                        add(1 + 3 * NTX + 2 * E::pair(i, s), E0 * cx.x);
+                        add(1 + 3 * NTX + 2 * E::pair(i, s) + 1, E0 * cx.y);
+                    }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            ws[E::O_AREF] = aref;
+            *cntp = 0;
+        }
+        __syncwarp();
+        return;
+    }
+    // General path: one queue entry per lane per round; the warp reduces every statistic right away (rare
+    // path: keep the register footprint small so that it does not limit the occupancy of the scan loop)
     // per round every lane drops the NACC contributions of its queue entry into a shared scratch
     // [NACC][32]; afterwards lane i sums statistic i over the lanes that held an entry (a transpose
     // instead of NACC butterfly reductions: ~25 stores + nround loads per lane, no shuffles)
@@ -794,14 +988,25 @@ cudaError_t launch_superimpose_stats(const Dims& d, int nb, const double* Xoff, 
 template <int NTX, int NRX>
 static cudaError_t run_heff(const Dims& d, int nb, const double* Yd, const double* PsiD, const double* theta,
                             const int32_t* active, const double* Xoff, double* qr, cudaStream_t s) {
+    static SmemOptIn optin_mma, optin;
     dim3 grid((d.T_d + 127) / 128, nb);
+    // tensor path once the contraction is a real GEMM: at least one full 8-column tile and two 8-deep steps
+    constexpr int NC = NTX * NRX, NT = (NC + 7) / 8;
+    const int KP = (d.N1 + 7) & ~7;
+    const size_t smem_mma = sizeof(cplx) * ((size_t)KP * (NT * 8 + 2) + 4 * 32 * (NC + 1));
+    if (NC >= 8 && d.N1 >= 16 && smem_mma <= 100 * 1024) {
+        cudaError_t e = opt_in_smem(optin_mma, (const void*)k_heff_qr_mma<NTX, NRX>, smem_mma);
+        if (e != cudaSuccess) return e;
+        k_heff_qr_mma<NTX, NRX><<<grid, 128, smem_mma, s>>>(d, (const cplx*)Yd, (const cplx*)PsiD, (const cplx*)theta,
+                                                            active, (const cplx*)Xoff, qr);
+        count_launch();
+        return cudaGetLastError();
+    }
     size_t smem = sizeof(cplx) * (size_t)d.L * NRX;
     const int use_smem = smem <= 64 * 1024;
     if (!use_smem) smem = 0;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_heff_qr<NTX, NRX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
+    cudaError_t e = opt_in_smem(optin, (const void*)k_heff_qr<NTX, NRX>, smem);
+    if (e != cudaSuccess) return e;
     k_heff_qr<NTX, NRX><<<grid, 128, smem, s>>>(d, (const cplx*)Yd, (const cplx*)PsiD, (const cplx*)theta, active,
                                                 (const cplx*)Xoff, qr, use_smem);
     count_launch();
