@@ -719,6 +719,363 @@ static cudaError_t run_chol3(const Dims& d, int nb, double* G, double* theta, co
     return cudaGetLastError();
 }
 
+// L2 cache-hinted 16-byte accesses (createpolicy + ld/st.global.L2::cache_hint)
+__device__ __forceinline__ unsigned long long l2_policy(bool keep) {
+    unsigned long long pol;
+    if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <int L2POL>
+__device__ __forceinline__ cplx ldg_c(const cplx* p, unsigned long long pol) {
+    if constexpr (L2POL == 0) {
+        return *p;
+    } else {
+        cplx v;
+        asm volatile("ld.global.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol) : "memory");
+        return v;
+    }
+}
+template <int L2POL>
+__device__ __forceinline__ void stg_c(cplx* p, cplx v, unsigned long long pol) {
+    if constexpr (L2POL == 0) {
+        *p = v;
+    } else {
+        asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_chol4: task pipeline of k_chol3 with TWO PANELS PER PASS over the factor.
+//
+// Measured (gpurun_out/r02b-r02c, 1184 trials): k_chol2 1.94 ms; k_chol3 with both operands through a cp.async
+// ring 2.1-2.8 ms (the ring costs L1: the block-row operand then misses); k_chol3 with register-fed operands
+// 2.03 ms, 1.89 ms with the 3-multiplication product.  Neither barriers nor DMMA count were the limiter: every
+// panel streams all previous columns of the rows below it from L2/DRAM (4.7 GB per launch, 7x the factor).
+// Halving that stream is what this kernel does: on EVEN panels k the update step takes the tile through
+// panels k+1 AND k+2 at once,
+//   S'[rows, panel k+1 | panel k+2] = A - C[rows, 0:g0] C[block rows k+1 | k+2, 0:g0]^H     (32 columns wide)
+// so the A fragments (the streamed operand) feed 16 instead of 8 DMMA quads per 8-column step; on ODD panels
+// only the missing 16-column slice is applied to panel k+2:  S' -= C[rows, k0:g0] C[block row, k0:g0]^H.
+// Same flags as k_chol3 plus "block row k+2 is final left of g0" (s_rowready2, set by tile 1).
+// ---------------------------------------------------------------------------
+template <bool GAUSS, int MINB, int PF, bool WIDE, bool BSPF, int L2POL>
+__global__ void __launch_bounds__(C3_WARPS * 32, MINB) k_chol4(Dims d, cplx* __restrict__ Gall,
+                                                               cplx* __restrict__ theta,
+                                                               const int32_t* __restrict__ active,
+                                                               int32_t* __restrict__ stat, cplx* th_global) {
+    constexpr int CH_THREADS = C3_WARPS * 32;
+    extern __shared__ __align__(16) double2 csm[];
+    const int b = blockIdx.x;
+    if (active != nullptr && active[b] == 0) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int Lp = d.Lp, Ltot = d.Ltot, ld = d.Lp;
+    cplx* A = Gall + (size_t)b * Ltot * Lp;
+    const int npan = (Lp + CH_NB - 1) / CH_NB;
+    const int nrb = (Ltot + 15) / 16 + 1;
+    // L2POL 1: the factors of every third trial are kept in L2 (evict_last), the others stream through it
+    // (evict_first): a cyclic working set of ~590 resident factors (340 MB) thrashes a 126 MB LRU completely,
+    // pinning a third of it turns a third of the operand stream into L2 hits.  L2POL 2: everything evict_first
+    // except the block rows (control experiment).
+    const unsigned long long pol = L2POL ? l2_policy(L2POL == 1 && (blockIdx.x % 3) == 0) : 0ull;
+
+    cplx* sD = csm;                                            // [16][17] diagonal block scratch
+    cplx* sWb = sD + CH_NB * CH_DS;                            // [3][16][17] inverses of the diagonal blocks
+    cplx* sTh = sWb + 3 * CH_NB * CH_DS;                       // [Lp][n_rx] solution vector (unless in global scratch)
+    int* s_prog = (int*)(sTh + (th_global ? 0 : Lp * d.n_rx)); // [nrb] panels completed per aligned 16-row block
+    int* s_adone = s_prog + nrb;                               // [npan] tiles of panel k past their triangular solve
+    int* s_start = s_adone + npan;                             // [npan + 1] first task id of panel k
+    __shared__ int s_next, s_bad;
+    __shared__ volatile int s_wready, s_rowready, s_rowready2;
+    __shared__ double s_maxpiv;
+
+    for (int i = tid; i < nrb + npan; i += CH_THREADS) s_prog[i] = 0;
+    if (tid == 0) {
+        s_next = 0; s_bad = 0; s_wready = 0; s_rowready = 0; s_rowready2 = 0; s_maxpiv = 0.0;
+        int acc = 0;
+        for (int k = 0; k < npan; ++k) {
+            s_start[k] = acc;
+            const int g0 = min(k * CH_NB + CH_NB, Lp);
+            acc += (Ltot - g0 + 15) >> 4;
+        }
+        s_start[npan] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double maxpiv = 0.0;
+        chol_diag_factor_reg(d, A, ld, 0, min(CH_NB, Lp), sD, sWb, lane, maxpiv, &s_bad);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) { s_maxpiv = maxpiv; s_wready = 1; }
+    }
+    __syncthreads();
+    const int ntasks = s_start[npan];
+
+    int myk = 0;
+    for (;;) {
+        int id = 0;
+        if (lane == 0) id = atomicAdd(&s_next, 1);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id >= ntasks) break;
+        while (id >= s_start[myk + 1]) ++myk;
+        const int k = myk, t = id - s_start[myk];
+        const int k0 = k * CH_NB;
+        const int nb = min(CH_NB, Lp - k0);
+        const int g0 = k0 + nb;                                   // first row below the diagonal block = next panel
+        const int nbn = (k + 1 < npan) ? min(CH_NB, Lp - g0) : 0;
+        const bool wide = WIDE && (k & 1) == 0;
+        // width of panel k+2 where this tile updates it as well (tile 0 sits above that panel's diagonal block)
+        const int nbn2 = (wide && t >= 1 && nbn == CH_NB && k + 2 < npan) ? min(CH_NB, Lp - (g0 + CH_NB)) : 0;
+        const int r0 = g0 + (t << 4);
+        const cplx* sW = sWb + (k % 3) * CH_NB * CH_DS;
+
+        if (k > 0) {
+            spin_until_ge((const volatile int*)&s_prog[r0 >> 4], k);
+            spin_until_ge((const volatile int*)&s_prog[(min(r0 + 16, Ltot) - 1) >> 4], k);
+        }
+        spin_until_ge(&s_wready, k + 1);
+
+        const int ra = min(r0 + g, Ltot - 1), rb8 = min(r0 + g + 8, Ltot - 1);
+        double cr[4][4], ci[4][4];
+        // ---- step A: X = S W^H on columns k0 .. k0+nb-1
+        {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { cr[j][e] = 0.0; ci[j][e] = 0.0; }
+            const cplx* pa0 = A + (size_t)ra * ld + k0 + tig;
+            const cplx* pa1 = A + (size_t)rb8 * ld + k0 + tig;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const int q0 = 8 * kk + tig;
+                cplx a0 = mk(0, 0), a1 = mk(0, 0), a2 = mk(0, 0), a3 = mk(0, 0);
+                if (q0 < nb) { a0 = ldg_c<L2POL>(pa0 + 8 * kk, pol); a1 = ldg_c<L2POL>(pa1 + 8 * kk, pol); }
+                if (q0 + 4 < nb) { a2 = ldg_c<L2POL>(pa0 + 8 * kk + 4, pol); a3 = ldg_c<L2POL>(pa1 + 8 * kk + 4, pol); }
+                const double ar[4] = {a0.x, a1.x, a2.x, a3.x};
+                const double ai[4] = {a0.y, a1.y, a2.y, a3.y};
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const cplx w0 = sW[(8 * j + g) * CH_DS + 8 * kk + tig];
+                    const cplx w1 = sW[(8 * j + g) * CH_DS + 8 * kk + tig + 4];
+                    dmma16x8x8(cr[j], ar, w0.x, w1.x);
+                    dmma16x8x8(ci[j], ai, w0.x, w1.x);
+                    dmma16x8x8(cr[j], ai, w0.y, w1.y);
+                    dmma16x8x8(ci[j], ar, -w0.y, -w1.y);
+                }
+            }
+            __syncwarp();  // all lanes have read S before anyone overwrites it
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int row = r0 + g + 8 * h;
+                    const int c = 8 * j + 2 * tig;
+                    if (row < Ltot && c < nb) {
+                        cplx* p2 = A + (size_t)row * ld + k0 + c;
+                        stg_c<L2POL>(p2, mk(cr[j][2 * h], ci[j][2 * h]), pol);
+                        stg_c<L2POL>(p2 + 1, mk(cr[j][2 * h + 1], ci[j][2 * h + 1]), pol);
+                    }
+                }
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicAdd(&s_adone[k], 1);
+        if (nbn == 0) continue;                                   // last panel: nothing left to update
+        if (lane == 0) {
+            if (t == 0) s_rowready = k + 1;                       // block row k+1 is final in columns < g0
+            // block row k+2 likewise; tiles (k, 1) of successive panels may finish out of order on the odd
+            // (narrow) panels, where nobody waits for them: keep the flag monotonic
+            if (t == 1) atomicMax((int*)&s_rowready2, k + 1);
+        }
+        if (t >= 1) spin_until_ge(&s_rowready, k + 1);
+        if (nbn2 > 0 && t >= 2) spin_until_ge(&s_rowready2, k + 1);
+        // ---- step B
+        {
+            const int qbeg = (WIDE && !wide) ? k0 : 0;            // odd panels: only the 16 columns of panel k are missing
+            const bool four = nbn2 > 0;                           // warp-uniform: panel k+2 is updated too
+            if (tig == 0) {   // the blocks to be updated are only needed at the very end: start fetching them now
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)ra * ld + g0));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)rb8 * ld + g0));
+            }
+            double p3[GAUSS ? 4 : 1][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { cr[j][e] = 0.0; ci[j][e] = 0.0; if (GAUSS) p3[GAUSS ? j : 0][e] = 0.0; }
+            const cplx* pa0 = A + (size_t)ra * ld + tig;
+            const cplx* pa1 = A + (size_t)rb8 * ld + tig;
+            const cplx* pb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pb[j] = A + (size_t)min(g0 + 8 * j + g, Ltot - 1) * ld + tig;
+            // fragments are double-buffered in registers: the loads of step q+1 are in flight during the DMMAs of
+            // step q (the tile rows stream from L2 / DRAM, the block rows hit L1)
+            constexpr int NJ = WIDE ? 4 : 2;
+            cplx fa[4], fb[NJ][2];
+            fa[0] = ldg_c<L2POL>(pa0 + qbeg, pol); fa[1] = ldg_c<L2POL>(pa1 + qbeg, pol);
+            fa[2] = ldg_c<L2POL>(pa0 + qbeg + 4, pol); fa[3] = ldg_c<L2POL>(pa1 + qbeg + 4, pol);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+                if (j < 2 || four) { fb[j][0] = pb[j][qbeg]; fb[j][1] = pb[j][qbeg + 4]; }
+            auto pair = [&](int j, const double (&ar)[4], const double (&ai)[4], const double (&as)[4], const cplx& b0,
+                            const cplx& b1) {
+                if (GAUSS) {
+                    dmma16x8x8(cr[j], ar, b0.x, b1.x);
+                    dmma16x8x8(ci[j], ai, b0.y, b1.y);
+                    dmma16x8x8(p3[GAUSS ? j : 0], as, b0.x - b0.y, b1.x - b1.y);
+                } else {
+                    dmma16x8x8(cr[j], ar, b0.x, b1.x);
+                    dmma16x8x8(ci[j], ai, b0.x, b1.x);
+                    dmma16x8x8(cr[j], ai, b0.y, b1.y);
+                    dmma16x8x8(ci[j], ar, -b0.y, -b1.y);
+                }
+            };
+            // L1 prefetch of the streamed operand PF steps ahead (no registers held): lanes 0-15 touch the line
+            // that holds the first, lanes 16-31 the line that holds the last element of their row's 128-byte segment
+            const cplx* ppf = A + (size_t)min(r0 + (lane & 15), Ltot - 1) * ld + ((lane >> 4) ? 7 : 0);
+#pragma unroll 1
+            for (int q0 = qbeg; q0 < g0; q0 += 8) {
+                cplx na[4], nbf[NJ][2];
+                const int qn = (q0 + 8 < g0) ? q0 + 8 : q0;   // last step reloads itself (harmless, L1 hit)
+                if (PF > 0 && q0 + 8 * PF < g0) asm volatile("prefetch.global.L1 [%0];" ::"l"(ppf + q0 + 8 * PF));
+                na[0] = ldg_c<L2POL>(pa0 + qn, pol); na[1] = ldg_c<L2POL>(pa1 + qn, pol);
+                na[2] = ldg_c<L2POL>(pa0 + qn + 4, pol); na[3] = ldg_c<L2POL>(pa1 + qn + 4, pol);
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+                    if (j < 2 || four) { nbf[j][0] = pb[j][qn]; nbf[j][1] = pb[j][qn + 4]; }
+                const double ar[4] = {fa[0].x, fa[1].x, fa[2].x, fa[3].x};
+                const double ai[4] = {fa[0].y, fa[1].y, fa[2].y, fa[3].y};
+                const double as[4] = {fa[0].x + fa[0].y, fa[1].x + fa[1].y, fa[2].x + fa[2].y, fa[3].x + fa[3].y};
+                pair(0, ar, ai, as, fb[0][0], fb[0][1]);
+                pair(1, ar, ai, as, fb[1][0], fb[1][1]);
+                if (WIDE && four) {
+                    pair(NJ - 2, ar, ai, as, fb[NJ - 2][0], fb[NJ - 2][1]);
+                    pair(NJ - 1, ar, ai, as, fb[NJ - 1][0], fb[NJ - 1][1]);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) fa[e] = na[e];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+                    if (j < 2 || four) { fb[j][0] = nbf[j][0]; fb[j][1] = nbf[j][1]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j >= 2 && !four) break;
+                const int cbase = g0 + 8 * j;                     // panel k+1: columns g0 .. ; panel k+2: g0 + 16 ..
+                const int width = (j < 2) ? g0 + nbn : g0 + CH_NB + nbn2;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int row = r0 + g + 8 * h;
+                    const int c = cbase + 2 * tig;
+                    if (row < Ltot && c < width) {
+                        cplx* p2 = A + (size_t)row * ld + c;
+                        const cplx v0 = ldg_c<L2POL>(p2, pol), v1 = ldg_c<L2POL>(p2 + 1, pol);
+                        double re0, im0, re1, im1;
+                        if (GAUSS) {
+                            re0 = cr[j][2 * h] + ci[j][2 * h];
+                            im0 = p3[GAUSS ? j : 0][2 * h] - cr[j][2 * h] + ci[j][2 * h];
+                            re1 = cr[j][2 * h + 1] + ci[j][2 * h + 1];
+                            im1 = p3[GAUSS ? j : 0][2 * h + 1] - cr[j][2 * h + 1] + ci[j][2 * h + 1];
+                        } else {
+                            re0 = cr[j][2 * h]; im0 = ci[j][2 * h]; re1 = cr[j][2 * h + 1]; im1 = ci[j][2 * h + 1];
+                        }
+                        stg_c<L2POL>(p2, mk(v0.x - re0, v0.y - im0), pol);
+                        stg_c<L2POL>(p2 + 1, mk(v1.x - re1, v1.y - im1), pol);
+                    }
+                }
+            }
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *((volatile int*)&s_prog[r0 >> 4]) = k + 1;
+        if (t == 0) {
+            // next diagonal block: its inverse goes into the ring slot last read by the tiles of panel k-2
+            if (k >= 2) spin_until_ge((const volatile int*)&s_adone[k - 2], s_start[k - 1] - s_start[k - 2]);
+            double maxpiv = s_maxpiv;
+            chol_diag_factor_reg(d, A, ld, g0, nbn, sD, sWb + ((k + 1) % 3) * CH_NB * CH_DS, lane, maxpiv, &s_bad);
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) { s_maxpiv = maxpiv; s_wready = k + 2; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && s_bad && stat) atomicOr(&stat[b], SBCE_ST_NOT_PD);
+
+    // ---- back substitution  C^H theta = z,  z[l][r] = conj(A[Lp + r][l])  (as in k_chol2).  The factor rows it
+    // walks were written long ago (592 resident factors do not fit L2): with BSPF the 16 rows of the NEXT block
+    // are pulled into L2 while the current block is processed.
+    cplx* th = th_global ? th_global + (size_t)b * d.Lp * d.n_rx : sTh;
+    const int nrx = d.n_rx;
+    for (int e = tid; e < Lp * nrx; e += CH_THREADS) {
+        const int l = e / nrx, r = e % nrx;
+        th[e] = cconj(A[(size_t)(Lp + r) * ld + l]);
+    }
+    for (int k0 = ((Lp - 1) / CH_NB) * CH_NB; k0 >= 0; k0 -= CH_NB) {
+        const int nb = min(CH_NB, Lp - k0);
+        if (BSPF && k0 >= CH_NB) {   // rows k0-16 .. k0-1, columns 0 .. k0-1: one 128-byte line per request
+            const int lines = (k0 * (int)sizeof(cplx) + 127) >> 7;
+            for (int e = tid; e < CH_NB * lines; e += CH_THREADS)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(A + (size_t)(k0 - CH_NB + e / lines) * ld) +
+                                                               ((size_t)(e % lines) << 7)));
+        }
+        __syncthreads();  // th updates of the previous block are complete
+        const bool act = tid < nb * nrx;
+        const int bc = act ? tid / nrx : 0, br = act ? tid % nrx : 0;
+        cplx xv = mk(0.0, 0.0);
+        if (act) {
+            const cplx* wrow = A + (size_t)(k0 + bc) * ld + k0;
+            xv = cscale(th[(k0 + bc) * nrx + br], 1.0 / wrow[bc].x);
+            for (int q = bc + 1; q < nb; ++q) cfmac(xv, th[(k0 + q) * nrx + br], wrow[q]);
+        }
+        __syncthreads();
+        if (act) th[(k0 + bc) * nrx + br] = xv;
+        __syncthreads();
+        for (int c = tid; c < k0; c += CH_THREADS) {
+            cplx cq[CH_NB];
+#pragma unroll
+            for (int q = 0; q < CH_NB; ++q) cq[q] = (q < nb) ? A[(size_t)(k0 + q) * ld + c] : mk(0.0, 0.0);
+            for (int r = 0; r < nrx; ++r) {
+                cplx v = th[c * nrx + r];
+#pragma unroll
+                for (int q = 0; q < CH_NB; ++q)
+                    if (q < nb) cfmsc(v, th[(k0 + q) * nrx + r], cq[q]);
+                th[c * nrx + r] = v;
+            }
+        }
+    }
+    __syncthreads();
+    cplx* out = theta + (size_t)b * d.L * nrx;
+    bool bad = false;
+    for (int e = tid; e < d.L * nrx; e += CH_THREADS) {
+        const cplx v = th[e];
+        out[e] = v;
+        if (!isfinite(v.x) || !isfinite(v.y)) bad = true;
+    }
+    if (bad && stat) atomicOr(&stat[b], SBCE_ST_NONFINITE);
+}
+
+template <bool GAUSS, int MINB, int PF, bool WIDE, bool BSPF, int L2POL = 0>
+static cudaError_t run_chol4(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
+                             double* th_scratch, cudaStream_t s) {
+    static SmemOptIn optin;
+    const int npan = (d.Lp + CH_NB - 1) / CH_NB, nrb = (d.Ltot + 15) / 16 + 1;
+    const size_t fixed = sizeof(cplx) * (size_t)(4 * CH_NB * CH_DS) + sizeof(int) * (size_t)(nrb + 2 * npan + 2);
+    const size_t thb = sizeof(cplx) * (size_t)d.Lp * d.n_rx;
+    // the solution vector sits in shared memory while that leaves most of the SM's L1 to the block-row operand
+    double* thg = nullptr;
+    size_t smem = fixed + thb;
+    if (smem > 24 * 1024) {
+        if (!th_scratch) return cudaErrorInvalidValue;
+        thg = th_scratch;
+        smem = fixed;
+    }
+    cudaError_t e = opt_in_smem(optin, (const void*)k_chol4<GAUSS, MINB, PF, WIDE, BSPF, L2POL>, smem);
+    if (e != cudaSuccess) return e;
+    k_chol4<GAUSS, MINB, PF, WIDE, BSPF, L2POL><<<nb, C3_WARPS * 32, smem, s>>>(d, (cplx*)G, (cplx*)theta, active, stat, (cplx*)thg);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, const int32_t* active, int32_t* stat,
                               double* th_scratch, cudaStream_t s) {
 #ifdef SBCE_DEV
@@ -735,6 +1092,20 @@ cudaError_t launch_chol_solve(const Dims& d, int nb, double* G, double* theta, c
         case 37: return run_chol3<0, true, 4>(d, nb, G, theta, active, stat, th_scratch, s);
         case 38: return run_chol3<0, true, 3>(d, nb, G, theta, active, stat, th_scratch, s);
         case 39: return run_chol3<0, false, 3>(d, nb, G, theta, active, stat, th_scratch, s);
+        // k_chol4<GAUSS, MINB, PF, WIDE, BSPF>
+        case 40: return run_chol4<false, 3, 0, true, false>(d, nb, G, theta, active, stat, th_scratch, s);
+        case 41: return run_chol4<true, 3, 0, true, false>(d, nb, G, theta, active, stat, th_scratch, s);
+        case 42: return run_chol4<false, 3, 2, true, true>(d, nb, G, theta, active, stat, th_scratch, s);
+        case 43: return run_chol4<true, 3, 2, true, true>(d, nb, G, theta, active, stat, th_scratch, s);
+        case 50: return run_chol4<true, 4, 0, false, false>(d, nb, G, theta, active, stat, th_scratch, s);   // = k_chol3<0,true,4>
+        case 51: return run_chol4<true, 4, 0, false, true>(d, nb, G, theta, active, stat, th_scratch, s);
+        case 52: return run_chol4<true, 4, 2, false, true>(d, nb, G, theta, active, stat, th_scratch, s);
+        case 53: return run_chol4<true, 4, 4, false, true>(d, nb, G, theta, active, stat, th_scratch, s);
+        case 54: return run_chol4<false, 4, 2, false, true>(d, nb, G, theta, active, stat, th_scratch, s);
+        case 55: return run_chol4<true, 3, 2, false, true>(d, nb, G, theta, active, stat, th_scratch, s);
+        case 56: return run_chol4<true, 4, 2, false, true, 1>(d, nb, G, theta, active, stat, th_scratch, s);
+        case 57: return run_chol4<true, 4, 2, false, true, 2>(d, nb, G, theta, active, stat, th_scratch, s);
+        case 58: return run_chol4<true, 4, 0, false, true, 1>(d, nb, G, theta, active, stat, th_scratch, s);
         default: break;
     }
 #endif

@@ -38,76 +38,97 @@ constexpr int RH_MAXR = 8;
 
 // The last CTA of every trial: right-hand side rows B^H stored under the matrix,
 //   row Lp + r, column l = n*n_tx + i :  conj(B[l][r]) = sum_t psi[t,n] conj(m_t[i] y_t[r]),
-// one thread per column l with n_rx accumulators, plus the identity padding of the trapezoid.
+// plus the identity padding of the trapezoid.  With Zc[t][i n_rx + r] = conj(m_t[i] y_t[r]) this is the complex
+// GEMM  Out (N+1 x n_tx n_rx) = Psi^T (N+1 x T) . Zc (T x n_tx n_rx)  and runs on the FP64 tensor path: a warp owns
+// one 16-row tile of RIS indices and two 8-column tiles; psi and Zc chunks are staged in shared memory (Zc rows
+// padded by two elements: conflict-free B fragments).  Its scalar predecessor -- one thread per column l, n_rx
+// complex accumulators, 5 shared loads per 4 complex FMAs -- executed 23 % of the Gram kernel's instructions
+// and held 21 % of its resident warp time (profiles/r02d) for 5 % of its arithmetic.
 template <int NTX>
 __device__ __forceinline__ void gram_rhs_cta(const Dims& d, int T, int b, cplx* sPsi, cplx* /*unused*/, const cplx* psi_b,
                                              const cplx* __restrict__ Y, const cplx* __restrict__ sm, const cplx* Gi,
                                              cplx* Gb) {
-    const int N1 = d.N1;
-    // Chunk length: as many symbols as the CTA's dynamic shared memory holds (the pair CTAs of the same launch
-    // size it for their operand ring).  profiles/r01m: with 16-symbol chunks this CTA -- one per trial, two
-    // barriers and a global-load round trip per chunk -- ran 2.6x longer than a pair CTA and held 23 % of the
-    // resident warp time while feeding the tensor pipe nothing; long chunks make it latency-cheap.
+    const int N1 = d.N1, n_rx = d.n_rx, L = d.L;
+    const int NC = NTX * n_rx;              // complex columns (i, r) -> i * n_rx + r
+    const int ZS = NC + 2;                  // padded row stride of the staged Zc
     unsigned dyn_bytes;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
-    const int per_sym = N1 + NTX * (d.n_rx > NTX ? d.n_rx : NTX);
-    int TCR = (int)(dyn_bytes / (sizeof(cplx) * per_sym));
-    TCR = max(1, min(TCR, 128));
-    cplx* sRr = sPsi + (size_t)TCR * N1;
-    // ---------------- right-hand side rows + padding
-    const int n_rx = d.n_rx, L = d.L;
+    // chunk length: as many symbols as the CTA's dynamic shared memory holds (the pair CTAs of the same launch
+    // size it for their operand ring), a multiple of 8 (one MMA k-step), at most 128
+    int TCR = (int)(dyn_bytes / (sizeof(cplx) * (N1 + ZS)));
+    TCR = max(8, min(TCR & ~7, 128));
+    cplx* sZ = sPsi + (size_t)TCR * N1;
     const cplx* m_b = sm + (size_t)b * T * NTX;
     const cplx* y_b = Y + (size_t)b * T * n_rx;
-    // each thread owns columns l and l + GR_THREADS of a 2*GR_THREADS-wide pass (one pass for L <= 512)
-    for (int l0 = 0; l0 < L; l0 += 2 * GR_THREADS) {
-        int ls[2], ns[2], is[2];
-        bool have[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    const int MT = (N1 + 15) >> 4, NTP = (NC + 15) >> 4;       // 16-row tiles, pairs of 8-column tiles
+    const int units = MT * NTP;
+    constexpr int NWARP = GR_THREADS / 32;
+    for (int u0 = 0; u0 < units; u0 += NWARP) {
+        const int u = u0 + warp;
+        const bool live = u < units;                            // warp-uniform
+        const int mt = live ? u / NTP : 0, np = live ? u % NTP : 0;
+        const int n0 = mt * 16, c0 = np * 16;
+        const int ra = min(n0 + g, N1 - 1), rb = min(n0 + g + 8, N1 - 1);     // clamped RIS rows (results discarded)
+        double cr[2][4], ci[2][4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            ls[u] = l0 + u * GR_THREADS + threadIdx.x;
-            have[u] = ls[u] < L;
-            ns[u] = have[u] ? ls[u] / NTX : 0;
-            is[u] = have[u] ? ls[u] % NTX : 0;
-        }
-        cplx acc[2][RH_MAXR];
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int r = 0; r < RH_MAXR; ++r) acc[u][r] = mk(0.0, 0.0);
+            for (int e = 0; e < 4; ++e) { cr[j][e] = 0.0; ci[j][e] = 0.0; }
         for (int t0 = 0; t0 < T; t0 += TCR) {
             const int tc = min(TCR, T - t0);
+            const int tc8 = (tc + 7) & ~7;
             __syncthreads();
-            for (int e = threadIdx.x; e < tc * N1; e += GR_THREADS) sPsi[e] = psi_b[(size_t)t0 * N1 + e];
-            for (int e = threadIdx.x; e < tc * NTX * n_rx; e += GR_THREADS) {
-                const int tt = e / (NTX * n_rx), ii = (e / n_rx) % NTX, r = e % n_rx;
-                sRr[e] = cconj(cmul(m_b[(size_t)(t0 + tt) * NTX + ii], y_b[(size_t)(t0 + tt) * n_rx + r]));
+            for (int e = threadIdx.x; e < tc8 * N1; e += GR_THREADS)
+                sPsi[e] = (e < tc * N1) ? psi_b[(size_t)t0 * N1 + e] : mk(0.0, 0.0);
+            for (int e = threadIdx.x; e < tc8 * ZS; e += GR_THREADS) {
+                const int tt = e / ZS, c = e % ZS;
+                cplx v = mk(0.0, 0.0);
+                if (tt < tc && c < NC) {
+                    const int ii = c / n_rx, r = c % n_rx;
+                    v = cconj(cmul(m_b[(size_t)(t0 + tt) * NTX + ii], y_b[(size_t)(t0 + tt) * n_rx + r]));
+                }
+                sZ[e] = v;
             }
             __syncthreads();
+            if (live) {
+                for (int ks = 0; ks < tc8; ks += 8) {
+                    const cplx* pl = sPsi + (size_t)(ks + tig) * N1;
+                    const cplx* ph = sPsi + (size_t)(ks + tig + 4) * N1;
+                    // A fragment order: (row g, k lo), (row g+8, k lo), (row g, k hi), (row g+8, k hi)
+                    const cplx a0 = pl[ra], a1 = pl[rb], a2 = ph[ra], a3 = ph[rb];
+                    const double ar[4] = {a0.x, a1.x, a2.x, a3.x};
+                    const double ai[4] = {a0.y, a1.y, a2.y, a3.y};
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (have[u]) {
-                    for (int tt = 0; tt < tc; ++tt) {
-                        const cplx p = sPsi[tt * N1 + ns[u]];
-                        const cplx* z = sRr + (tt * NTX + is[u]) * n_rx;
-#pragma unroll
-                        for (int r = 0; r < RH_MAXR; ++r)
-                            if (r < n_rx) cfma(acc[u][r], p, z[r]);
+                    for (int j = 0; j < 2; ++j) {
+                        const int c = min(c0 + 8 * j + g, ZS - 1);           // columns >= NC hold zeros
+                        const cplx b0 = sZ[(size_t)(ks + tig) * ZS + c], b1 = sZ[(size_t)(ks + tig + 4) * ZS + c];
+                        // (ar + i ai)(br + i bi): re += ar br - ai bi ; im += ar bi + ai br
+                        dmma16x8x8(cr[j], ar, b0.x, b1.x);
+                        dmma16x8x8(ci[j], ar, b0.y, b1.y);
+                        dmma16x8x8(cr[j], ai, -b0.y, -b1.y);
+                        dmma16x8x8(ci[j], ai, b0.x, b1.x);
                     }
                 }
             }
         }
+        if (live) {
+            // accumulator (row g + 8h, columns 8 j + 2 tig, + 1) -> G[(Lp + r) * Lp + n * NTX + i]
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (have[u]) {
+            for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int r = 0; r < RH_MAXR; ++r)
-                    if (r < n_rx) {
-                        const size_t o = (size_t)(d.Lp + r) * d.Lp + ls[u];
-                        cplx v = acc[u][r];
-                        if (Gi) v = cadd(v, Gi[o]);
-                        Gb[o] = v;
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int n = n0 + g + 8 * h, c = c0 + 8 * j + 2 * tig + e;
+                        if (n < N1 && c < NC) {
+                            const int ii = c / n_rx, r = c % n_rx;
+                            const size_t o = (size_t)(d.Lp + r) * d.Lp + (n * NTX + ii);
+                            cplx v = mk(cr[j][2 * h + e], ci[j][2 * h + e]);
+                            if (Gi) v = cadd(v, Gi[o]);
+                            Gb[o] = v;
+                        }
                     }
-            }
         }
     }
     // padding: identity on the padded diagonal rows L..Lp-1, zero padded columns / rows of B^H
@@ -155,7 +176,7 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_gram(Dims d, int T, int TC, c
     const bool is_pair = item < P;
     int n = 0, np = 0;
     if (is_pair) {
-        n = (int)((sqrt(8.0 * item + 1.0) - 1.0) * 0.5);
+        n = (int)((sqrtf(8.0f * (float)item + 1.0f) - 1.0f) * 0.5f);   // the two loops below make it exact
         while ((n + 1) * (n + 2) / 2 <= item) ++n;
         while (n * (n + 1) / 2 > item) --n;
         np = item - n * (n + 1) / 2;
@@ -340,7 +361,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) k_gram_tma4(Dims d, int T, cons
             int item = blockIdx.x * GR_THREADS + (2 * warp + u) * 16 + g + 8 * h;
             pv[u][h] = item < P;
             item = min(item, P - 1);
-            int n = (int)((sqrt(8.0 * item + 1.0) - 1.0) * 0.5);
+            int n = (int)((sqrtf(8.0f * (float)item + 1.0f) - 1.0f) * 0.5f);   // made exact by the loops below
             while ((n + 1) * (n + 2) / 2 <= item) ++n;
             while (n * (n + 1) / 2 > item) --n;
             pn[u][h] = n;
@@ -348,13 +369,38 @@ __global__ void __launch_bounds__(GT_THREADS, 2) k_gram_tma4(Dims d, int T, cons
         }
     }
     const int boff0 = gram_bcol_offset(g), boff1 = gram_bcol_offset(8 + g);
+    // The accumulators START from the pilot part G_p instead of adding it in the epilogue: its loads are issued
+    // here, before the first wait on the operand ring, where their latency is hidden behind the TMA prologue
+    // (in the epilogue they were 8 % of the kernel's stall samples, profiles/r02d).  An upper pair (i<j) is kept
+    // as U = sum pr Rr, W = sum pr Ri, Z = sum pi Rr, V = sum pi Ri with out_ij = (U - V, W + Z) and
+    // out_ji = (U + V, Z - W): starting from U = (a.x + b.x)/2, V = (b.x - a.x)/2, W = (a.y - b.y)/2,
+    // Z = (a.y + b.y)/2 yields a = G_p[ij], b = G_p[ji] (to one rounding of the larger of the two).
     double accr[2][2][4], acci[2][2][4];  // [tile][n-tile][c0..c3]
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
+        for (int h = 0; h < 2; ++h) {
+            const bool on = Gi != nullptr && pv[u][h];
+            const cplx* gp = on ? Gi + (size_t)(pn[u][h] * NTX) * d.Lp + pnp[u][h] * NTX : nullptr;
+            auto gi = [&](int i, int j) { return on ? gp[(size_t)i * d.Lp + j] : mk(0.0, 0.0); };
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { accr[u][nt][e] = 0.0; acci[u][nt][e] = 0.0; }
+            for (int nt = 0; nt < 2; ++nt) {
+                const int col = 8 * nt + 2 * tig;
+                double r0, r1, i0, i1;
+                if (col < 4) {
+                    const cplx a = gi(col, col), c2 = gi(col + 1, col + 1);
+                    r0 = a.x; i0 = a.y; r1 = c2.x; i1 = c2.y;
+                } else {
+                    const int q = (col - 4) >> 1;
+                    const int qi = (q < 3) ? 0 : (q < 5 ? 1 : 2);
+                    const int qj = (q < 3) ? q + 1 : (q < 5 ? q - 1 : 3);
+                    const cplx a = gi(qi, qj), c2 = gi(qj, qi);
+                    r0 = 0.5 * (a.x + c2.x); i1 = 0.5 * (c2.x - a.x); r1 = 0.5 * (a.y - c2.y); i0 = 0.5 * (a.y + c2.y);
+                }
+                accr[u][nt][2 * h] = r0; accr[u][nt][2 * h + 1] = r1;
+                acci[u][nt][2 * h] = i0; acci[u][nt][2 * h + 1] = i1;
+            }
+        }
 
     for (int ck = 0; ck < nchunk; ++ck) {
         const int s = ck % GT_STAGES;
@@ -398,11 +444,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) k_gram_tma4(Dims d, int T, cons
         for (int h = 0; h < 2; ++h) {
             if (!pv[u][h]) continue;
             const int n = pn[u][h], np = pnp[u][h];
-            auto put = [&](int i, int j, cplx v) {
-                const size_t o = (size_t)(n * NTX + i) * d.Lp + (np * NTX + j);
-                if (Gi) v = cadd(v, Gi[o]);
-                Gb[o] = v;
-            };
+            auto put = [&](int i, int j, cplx v) { Gb[(size_t)(n * NTX + i) * d.Lp + (np * NTX + j)] = v; };
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
                 const double r0 = accr[u][nt][2 * h], r1 = accr[u][nt][2 * h + 1];
@@ -478,7 +520,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_gram_mma(Dims d, int T, int T
         int item = blockIdx.x * GW_PAIRS + warp * 16 + g + 8 * h;
         pv[h] = item < P;
         item = min(item, P - 1);
-        int n = (int)((sqrt(8.0 * item + 1.0) - 1.0) * 0.5);
+        int n = (int)((sqrtf(8.0f * (float)item + 1.0f) - 1.0f) * 0.5f);   // made exact by the loops below
         while ((n + 1) * (n + 2) / 2 <= item) ++n;
         while (n * (n + 1) / 2 > item) --n;
         pn[h] = n;
@@ -565,6 +607,9 @@ __global__ void __launch_bounds__(GR_THREADS, 1) k_gram_mma(Dims d, int T, int T
     }
 }
 
+// shared memory the right-hand-side CTA needs at least: one 8-symbol MMA step of psi and of the padded Zc rows
+static size_t rhs_smem_min(int N1, int ntx, int n_rx) { return sizeof(cplx) * (size_t)(8 * (N1 + ntx * n_rx + 2)); }
+
 // largest chunk length (multiple of 8, at most 32) whose two stages fit in `budget` bytes
 static int gram_chunk(int N1, int ntx, size_t budget) {
     int tc = 32;
@@ -585,9 +630,8 @@ static cudaError_t run_gram_wide(const Dims& d, int nb, const double* Psi, int T
     dim3 grid((P + GW_PAIRS - 1) / GW_PAIRS + 1, nb);   // + 1: the right-hand-side / padding CTA
     int tc = gram_chunk(d.N1, NTX, 100 * 1024);
     if (sizeof(cplx) * (size_t)(2 * tc * (d.N1 + NTX * NTX)) > 227 * 1024) return cudaErrorInvalidValue;
-    const int zsz = NTX * (d.n_rx > NTX ? d.n_rx : NTX);
     size_t smem = sizeof(cplx) * (size_t)(2 * tc * (d.N1 + NTX * NTX));
-    const size_t smem_rhs = sizeof(cplx) * (size_t)(GR_TC * d.N1 + GR_TC * zsz);
+    const size_t smem_rhs = 2 * rhs_smem_min(d.N1, NTX, d.n_rx);                    // 16-symbol chunks at least
     if (smem_rhs > smem) smem = smem_rhs;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = opt_in_smem(optin, (const void*)k_gram_mma<NTX>, smem);
@@ -608,9 +652,8 @@ static cudaError_t run_gram_scalar(const Dims& d, int nb, const double* Psi, int
     dim3 grid((P + GR_THREADS - 1) / GR_THREADS + 1, nb);   // + 1: the right-hand-side / padding CTA
     int tc = GR_TC;
     while (tc > 2 && sizeof(cplx) * (size_t)(2 * tc * (d.N1 + NTX * NTX)) > 100 * 1024) tc >>= 1;
-    const int zsz = NTX * (d.n_rx > NTX ? d.n_rx : NTX);
     size_t smem = sizeof(cplx) * (size_t)(2 * tc * (d.N1 + NTX * NTX));          // two cp.async stages (pair CTAs)
-    const size_t smem_rhs = sizeof(cplx) * (size_t)(d.N1 + zsz);                  // rhs CTA: at least one symbol
+    const size_t smem_rhs = rhs_smem_min(d.N1, NTX, d.n_rx);                      // rhs CTA: one MMA step at least
     if (smem_rhs > smem) smem = smem_rhs;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = opt_in_smem(optin, (const void*)k_gram<NTX>, smem);
@@ -631,8 +674,7 @@ static cudaError_t run_gram4(const Dims& d, int nb, const double* Psi, int T, co
     if (smem > 160 * 1024) return run_gram_wide<4>(d, nb, Psi, T, sR, Y, sm, Ginit, Gout, active, s);
     const int P = d.N1 * (d.N1 + 1) / 2;
     dim3 grid((P + GR_THREADS - 1) / GR_THREADS + 1, nb);   // + 1: the right-hand-side / padding CTA
-    const int zsz = NTX * (d.n_rx > NTX ? d.n_rx : NTX);
-    const size_t smem_rhs = sizeof(cplx) * (size_t)(GR_TC * d.N1 + GR_TC * zsz);
+    const size_t smem_rhs = 2 * rhs_smem_min(d.N1, NTX, d.n_rx);
     if (smem_rhs > smem) smem = smem_rhs;
     cudaError_t e = opt_in_smem(optin, (const void*)k_gram_tma4, smem);
     if (e != cudaSuccess) return e;

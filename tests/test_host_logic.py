@@ -237,3 +237,17 @@ def test_em_parallel_validates_shapes_before_touching_the_device():
         sbce.em_parallel(Y, 6, None, [], [], 0, 5, 1, np.ones((4, 5), complex), table, 4, 0.1, 2, 3)   # T mismatch
     with pytest.raises(ValueError):
         sbce.em_parallel(Y, 5, None, [], [], 0, 5, 1, np.ones((3, 5), complex), table, 4, 0.1, 2, 3)   # N+1 rows expected
+
+
+def test_finish_reports_nan_ser_for_points_without_decisions():
+    """drivers._finish: points whose estimator takes no joint decision (PM modes) have no symbol counts; the SER
+    curves must read NaN there instead of 0, the NMSE stays the mean over valid trials (single rank: no collective)."""
+    from sbce.drivers import PointResult, _finish
+
+    a = PointResult(nmse_sum=0.6, n_valid=3.0, n_flagged=1.0, sym_err=5.0, sym_total=50.0, ser_coded_sum=0.9, n_trials=4.0)
+    b = PointResult(nmse_sum=0.2, n_valid=4.0, n_flagged=0.0, n_trials=4.0)
+    out = _finish([10, 20], [a, b], device=None)
+    np.testing.assert_allclose(out["nmse"], [0.2, 0.05])
+    assert out["ser"][0] == 0.1 and np.isnan(out["ser"][1])
+    assert abs(out["ser_as_coded"][0] - 0.225) < 1e-15 and np.isnan(out["ser_as_coded"][1])
+    assert list(out["n_flagged"]) == [1.0, 0.0]
