@@ -56,6 +56,8 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+constexpr int RH_MAXR = 8;   // receive antennas supported by the normal-equation / solve kernels
+
 // Problem dimensions resolved once on the host and passed by value to kernels.
 struct Dims {
     int N, N1, n_tx, n_rx, M, sqM, bitsM, T_p, T_d, itera;

@@ -778,8 +778,9 @@ struct Scan {
     }
 };
 
-template <int NTX, int SQM, bool HARD, int WARPS, int MINB = (NTX > 4 ? 2 : 4)>
-__global__ void __launch_bounds__(WARPS * 32, MINB) k_enum(Dims d, const double* __restrict__ qr,
+// (4 CTAs per SM at 128 registers with a few spilled words beat 3 CTAs at 140 registers without: 1.16 vs 1.22 ms)
+template <int NTX, int SQM, bool HARD, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (NTX > 4 ? 2 : 4)) k_enum(Dims d, const double* __restrict__ qr,
                                                      const double* __restrict__ varn,
                                                      const int32_t* __restrict__ active, cplx* __restrict__ stat_m,
                                                      cplx* __restrict__ stat_R, int32_t* __restrict__ kstar,
@@ -1042,16 +1043,6 @@ static cudaError_t run_enum(const Dims& d, int nb, const double* qr, const doubl
         k_enum<NTX, SQM, true, WARPS><<<grid, WARPS * 32, smem, s>>>(d, qr, varn, active, (cplx*)stat_m,
                                                                       (cplx*)stat_R, kstar, lse_sym);
     } else {
-#ifdef SBCE_DEV
-        if constexpr (NTX == 4 && SQM == 4) {
-            if (dev_knob("SBCE_ENUM_MINB", 4) == 3) {   // tuning builds: 168 registers, no spills, 3 CTAs per SM
-                k_enum<NTX, SQM, false, WARPS, 3><<<grid, WARPS * 32, smem, s>>>(d, qr, varn, active, (cplx*)stat_m,
-                                                                                  (cplx*)stat_R, kstar, lse_sym);
-                count_launch();
-                return cudaGetLastError();
-            }
-        }
-#endif
         if (smem > 48 * 1024) {
             e = cudaFuncSetAttribute(k_enum<NTX, SQM, false, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;

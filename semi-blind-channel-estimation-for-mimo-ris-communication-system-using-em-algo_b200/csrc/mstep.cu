@@ -34,7 +34,6 @@ namespace sbce {
 constexpr int GR_THREADS = 256;
 constexpr int GR_TC = 16;  // symbols per shared-memory chunk (default; shrunk at launch for very long psi rows)
 
-constexpr int RH_MAXR = 8;
 
 // The last CTA of every trial: right-hand side rows B^H stored under the matrix,
 //   row Lp + r, column l = n*n_tx + i :  conj(B[l][r]) = sum_t psi[t,n] conj(m_t[i] y_t[r]),
@@ -48,7 +47,7 @@ template <int NTX>
 __device__ __forceinline__ void gram_rhs_cta(const Dims& d, int T, int b, cplx* sPsi, cplx* /*unused*/, const cplx* psi_b,
                                              const cplx* __restrict__ Y, const cplx* __restrict__ sm, const cplx* Gi,
                                              cplx* Gb) {
-    const int N1 = d.N1, n_rx = d.n_rx, L = d.L;
+    const int N1 = d.N1, n_rx = d.n_rx;
     const int NC = NTX * n_rx;              // complex columns (i, r) -> i * n_rx + r
     const int ZS = NC + 2;                  // padded row stride of the staged Zc
     unsigned dyn_bytes;
