@@ -10,8 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# SBCE_LIBRARY selects another build of the same library (tools/build_dev.sh: tuning build with kernel-variant knobs)
-LIB_PATH = os.environ.get("SBCE_LIBRARY") or os.path.join(HERE, "libsbce.so")
+LIB_PATH = os.path.join(HERE, "libsbce.so")
 
 MODE_SOFT, MODE_HARD, MODE_PM, MODE_PM_BETA, MODE_ZF, MODE_MMSE = 0, 1, 2, 3, 4, 5
 FLAG_GENIE_STOP, FLAG_QUIRKS, FLAG_PSI_SHARED, FLAG_ZERO_START, FLAG_FULL_SCAN, FLAG_SUPERIMPOSED = 1, 2, 4, 8, 16, 32

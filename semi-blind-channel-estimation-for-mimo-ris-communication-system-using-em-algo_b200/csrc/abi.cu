@@ -4,7 +4,6 @@
 #include <mutex>
 #include <vector>
 #include <stdio.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -13,13 +12,6 @@ namespace sbce {
 
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
-
-#ifdef SBCE_DEV
-int dev_knob(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
-#endif
 
 // ---- optional per-phase CUDA-event timing (bench.py's roofline numbers) --------------------------
 // Events are recorded on the launch stream around every phase while profiling is on; the cost is one

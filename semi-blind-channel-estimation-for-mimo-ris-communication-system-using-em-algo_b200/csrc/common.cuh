@@ -138,11 +138,6 @@ cudaError_t launch_accumulate_ser(const Dims& d, int nb, const int32_t* kstar, c
 
 void count_launch(int n = 1);
 
-#ifdef SBCE_DEV
-// Tuning builds only (-DSBCE_DEV, tools/build_dev.sh -> libsbce_dev.so): integer knob from the environment, read
-// once.  The shipped library is compiled without SBCE_DEV and contains no run-time kernel switches.
-int dev_knob(const char* name, int dflt);
-#endif
 
 // Opt-in to more than 48 KB of dynamic shared memory, once per (kernel instantiation, device) instead of on
 // every launch of the EM loop.  Each launcher keeps one `static SmemOptIn` per kernel it launches.

@@ -887,8 +887,30 @@ __global__ void __launch_bounds__(WARPS * 32, (NTX > 4 ? 2 : 4)) k_enum(Dims d, 
         sc.lim = HARD ? base : base + sc.thr;
     }
 
+    // Top-level pre-pass (prefixes of two or more streams): lane m tests the FIRST prefix stream's symbol m against
+    // the Babai bound once.  A round of 32 prefixes whose top symbols are all dead would only compute its prefix
+    // levels to find every lane dead; it is skipped outright.  Dead under the initial bound implies dead under any
+    // later (tighter) one, and a dead round contributes nothing in either mode, so the sequence of visited live
+    // nodes -- hence the queue order and every output bit -- is unchanged.
+    unsigned top_alive = 0xffffffffu;
+    constexpr int TOP_SHIFT = E::BITS * (E::PL - 1);
+    if (E::PL >= 2 && sc.prune) {
+        bool a = false;
+        if (lane < M) {
+            const double* gs = g + (NTX - 1) * SQM;
+            const double eI = yt[NTX - 1].x - gs[lane & (SQM - 1)];
+            const double eQ = yt[NTX - 1].y - gs[lane >> E::HB];
+            a = !(c0 + fma(eI, eI, eQ * eQ) > sc.lim);
+        }
+        top_alive = __ballot_sync(0xffffffffu, a);
+    }
     // all lanes iterate the same number of prefixes (invalid ones carry an infinite partial distance)
     for (int pb = 0; pb < E::NPREF; pb += 32) {
+        if (E::PL >= 2) {
+            const int lo = pb >> TOP_SHIFT, hi = min(pb + 31, E::NPREF - 1) >> TOP_SHIFT;
+            const unsigned bits = (hi >= 31 ? 0xffffffffu : ((2u << hi) - 1u)) & ~((1u << lo) - 1u);
+            if ((top_alive & bits) == 0u) continue;
+        }
         const int p = pb + lane;
         const bool valid = p < E::NPREF;
         sc.template prefix<NTX - 1, E::PL>(yt, c0, 0, valid ? p : 0, r01, !valid);
