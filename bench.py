@@ -170,6 +170,16 @@ def workload_dict(w):
     return d
 
 
+def cpu_sample(wd, sample_iters, seed=1234):
+    """One bounded sample of the CPU arm (oracle/cpu_bench.py) in a FRESH interpreter: the worker pool is forked
+    from a process without a CUDA context or pinned buffers (forking the GPU process cost ~80 s per pool)."""
+    out = subprocess.run([sys.executable, "-m", "oracle.cpu_bench", json.dumps(wd), str(int(sample_iters)), str(int(seed))],
+                         cwd=ROOT, capture_output=True, text=True, timeout=1800)
+    if out.returncode != 0:
+        raise RuntimeError("cpu_bench failed: " + out.stderr[-800:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
 # ---------------------------------------------------------------------------
 # reference arm (CPU)
 # ---------------------------------------------------------------------------
@@ -181,13 +191,13 @@ def run_reference(args):
     import importlib
 
     workloads = importlib.import_module("sbce").workloads      # shapes only: nothing of the product runs here
-    from oracle import cpu_bench
 
     w = workloads.WORKLOADS[args.config]
     wd = workload_dict(w)
     vals, last = [], None
     for i in range(args.warmup + args.steps):
-        r = cpu_bench.time_sample(wd, sample_iters=args.cpu_sample_iters, workers=None, seed=1000 + 97 * i)
+        # warm-up steps (untimed) run one EM iteration per worker, timed steps the bounded sample
+        r = cpu_sample(wd, args.cpu_sample_iters if i >= args.warmup else 1, seed=1000 + 97 * i)
         if i >= args.warmup:
             vals.append(r)
         last = r
@@ -562,9 +572,7 @@ def run_ours(args):
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
     cpu = None
     if world == 1 and not (args.no_cpu_baseline or args.kernels_only):
-        from oracle import cpu_bench
-
-        r = cpu_bench.time_sample(workload_dict(w), sample_iters=args.cpu_sample_iters, workers=None)
+        r = cpu_sample(workload_dict(w), args.cpu_sample_iters)
         cpu = dict(value=r["trials_per_s"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"],
                    seconds=r["seconds"])
 

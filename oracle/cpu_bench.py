@@ -90,3 +90,19 @@ def time_sample(w, sample_iters=2, workers=None, seed=1234):
                        "n_tx=%d, mode %s), scaled x%g"
                        % (workers, sample_iters, itera, "zero" if w.get("zero_start") else "LS", w["T_d"], w["M"],
                           w["n_tx"], w.get("mode", "soft"), itera / float(sample_iters)))
+
+
+def main(argv=None):
+    """CLI used by bench.py (a FRESH process: forking the GPU process with its pinned buffers and CUDA context
+    costs tens of seconds per pool):  python -m oracle.cpu_bench '<workload json>' <sample_iters> [seed]"""
+    import json
+    import sys
+
+    argv = sys.argv[1:] if argv is None else argv
+    w = json.loads(argv[0])
+    r = time_sample(w, sample_iters=int(argv[1]), workers=None, seed=int(argv[2]) if len(argv) > 2 else 1234)
+    print(json.dumps(r))
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,10 @@ ESTEP_CASES = [
     # wide arrays (BASELINE.json configs 4/5: 8x8): row-per-lane QR + deep hypothesis trees
     (6, 5, 5, 4, 9, 0.3), (5, 6, 6, 4, 7, 0.2), (5, 7, 8, 4, 6, 0.4), (6, 8, 8, 4, 9, 0.3), (6, 8, 8, 4, 5, 20.0),
     (4, 5, 6, 16, 3, 0.6), (4, 6, 4, 4, 5, 0.5), (5, 5, 7, 4, 18, 0.2),
+    # tensor-path effective-channel kernel (n_tx n_rx >= 8, N >= 15): 1..4 column tiles, ragged K (N + 1 not a
+    # multiple of 8), symbol counts that are not multiples of 16 / 32 / 128
+    (15, 1, 8, 4, 37, 0.3), (17, 2, 4, 16, 33, 0.4), (20, 3, 4, 4, 40, 0.3), (16, 4, 4, 4, 130, 0.2),
+    (23, 4, 6, 4, 19, 0.3), (18, 3, 8, 4, 21, 0.4), (31, 4, 8, 4, 45, 0.3), (40, 2, 6, 16, 29, 0.5),
 ]
 
 
@@ -388,6 +392,14 @@ BATCH_CASES = [
     (6, 8, 8, 4, 64, 80, 2, 0.3, "hard"),
     (5, 6, 8, 4, 40, 50, 3, 0.5, "soft"),
     (4, 5, 5, 16, 30, 10, 2, 0.8, "soft"),       # 5 streams of 16-QAM: K = 2^20
+    # small shapes that run the kernels of the headline path end to end (tensor-path effective channel, TMA Gram
+    # with its DMMA right-hand-side CTA, task-pipeline Cholesky with the solution vector in shared memory)
+    # (T_p = 10 N: the PM.py pilot design repeats with period N and leaves the last RIS element unobserved; every
+    # phase row then meets enough independent pilot vectors for pinv() to have a clean rank gap)
+    (16, 4, 4, 4, 160, 48, 3, 0.3, "soft"),
+    (16, 4, 4, 4, 160, 72, 3, 0.3, "hard"),
+    (20, 4, 4, 16, 100, 96, 2, 0.2, "soft"),
+    (24, 3, 4, 4, 144, 90, 3, 0.3, "soft"),
 ]
 
 

@@ -6,7 +6,7 @@
 Counts: DMMA = FP64 tensor-pipe MMA (DMMA.8x8x4; mma.sync.m16n8k8.f64 is issued as four of them),
 UBLKCP = TMA bulk copy (cp.async.bulk), SYNCS = mbarrier operations, LDGSTS = cp.async, BAR = CTA barriers.
 Excerpts: for the kernels listed in HOT the basic block with the most DMMA instructions (the steady-state
-inner loop), instruction text only, so that the operand feeding (LDS / LDGSTS / UBLKCP) next to the MMAs is
+inner loop: blocks ending in a backward branch are preferred), instruction text only, so that the operand feeding (LDS / LDGSTS / UBLKCP) next to the MMAs is
 visible, not just counted.
 """
 import collections
@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(
     ROOT, "semi-blind-channel-estimation-for-mimo-ris-communication-system-using-em-algo_b200", "libsbce.so")
 MNEMS = ["DMMA", "UBLKCP", "SYNCS", "LDGSTS", "DFMA", "DADD", "LDS", "SHFL", "BAR"]
-HOT = ["k_gram_tma4", "k_chol3", "k_chol2", "k_heff_qr_mma<4, 4>", "k_enum<4, 4, false"]
+HOT = ["k_gram_tma4", "k_chol_solve", "k_heff_qr_mma<4, 4>", "k_enum<4, 4, false"]
 
 
 def demangle(n):
@@ -74,7 +74,11 @@ def main():
                     curb = []
             if curb:
                 blocks.append(curb)
-            best = max(blocks, key=lambda bl: sum(1 for _, t in bl if "DMMA" in t or "UBLKCP" in t))
+            def is_loop(bl):   # ends in a backward branch
+                m = re.search(r"BRA(?:\.\w+)*\s+(?:\S+,\s*)?(0x[0-9a-f]+)", bl[-1][1])
+                return bool(m) and int(m.group(1), 16) <= bl[-1][0]
+
+            best = max(blocks, key=lambda bl: sum(1 for _, t in bl if "DMMA" in t or "UBLKCP" in t) * (1.0 if is_loop(bl) else 0.3))
             nd = sum(1 for _, t in best if "DMMA" in t)
             if nd == 0 and "enum" not in name:
                 continue
