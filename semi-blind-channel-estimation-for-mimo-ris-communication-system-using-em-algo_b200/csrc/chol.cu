@@ -123,6 +123,14 @@ __device__ __forceinline__ void chol_diag_factor_reg(const Dims& d, cplx* A, int
     __syncwarp();
 }
 
+#ifdef SBCE_CHOL_LOADS_FIRST
+// volatile: keeps its place among the (volatile) MMAs, i.e. at the top of the step
+__device__ __forceinline__ cplx ldg_v(const cplx* p) {
+    cplx v;
+    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+#endif
 __device__ __forceinline__ void spin_until_ge(const volatile int* p, int v) {
     while (*p < v) __nanosleep(20);
     __threadfence_block();

@@ -237,6 +237,11 @@ __global__ void __launch_bounds__(128, 4) k_heff_qr_mma(Dims d, const cplx* __re
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int h = 0; h < 2; ++h) prow[mt][h] = psi_b + (size_t)min(t0 + mt * 16 + g + 8 * h, d.T_d - 1) * N1;
+    {   // pull this warp's 32 phase rows into L2 before the k loop touches them (lane = row): the fragment loads
+        // below are then L2 hits instead of DRAM round trips (0.200 -> 0.174 ms at the north-star size)
+        const char* rowp = (const char*)(psi_b + (size_t)min(t0 + lane, d.T_d - 1) * N1);
+        for (int o = 0; o < N1 * (int)sizeof(cplx); o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + o));
+    }
     double cr[2][NT][4], ci[2][NT][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -1056,19 +1061,16 @@ static cudaError_t run_enum(const Dims& d, int nb, const double* qr, const doubl
     constexpr int WARPS = 4;
     dim3 grid((d.T_d + WARPS - 1) / WARPS, nb);
     constexpr size_t smem = sizeof(double) * WARPS * EnumT<NTX, SQM>::WS_DOUBLES;
+    static SmemOptIn optin_hard, optin_soft;
     cudaError_t e;
     if (d.mode == SBCE_MODE_HARD) {
-        if (smem > 48 * 1024) {
-            e = cudaFuncSetAttribute(k_enum<NTX, SQM, true, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
+        e = opt_in_smem(optin_hard, (const void*)k_enum<NTX, SQM, true, WARPS>, smem);
+        if (e != cudaSuccess) return e;
         k_enum<NTX, SQM, true, WARPS><<<grid, WARPS * 32, smem, s>>>(d, qr, varn, active, (cplx*)stat_m,
                                                                       (cplx*)stat_R, kstar, lse_sym);
     } else {
-        if (smem > 48 * 1024) {
-            e = cudaFuncSetAttribute(k_enum<NTX, SQM, false, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
+        e = opt_in_smem(optin_soft, (const void*)k_enum<NTX, SQM, false, WARPS>, smem);
+        if (e != cudaSuccess) return e;
         k_enum<NTX, SQM, false, WARPS><<<grid, WARPS * 32, smem, s>>>(d, qr, varn, active, (cplx*)stat_m,
                                                                        (cplx*)stat_R, kstar, lse_sym);
     }
