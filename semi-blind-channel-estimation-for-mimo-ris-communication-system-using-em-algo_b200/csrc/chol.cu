@@ -40,6 +40,7 @@
 //   L2 evict_last on every third trial / evict_first stream (createpolicy + cache_hint)          1.84 ms (+-0)
 //   L2 prefetch of the next block's rows in the back substitution                                      +-0
 //   back substitution as a separate warp-per-trial kernel                                          1.96 ms
+//   next step's fragment loads pinned to the top of the step (volatile asm; ptxas sinks them)   1.86 ms (+-0)
 #include <math.h>
 
 #include "common.cuh"
@@ -123,14 +124,6 @@ __device__ __forceinline__ void chol_diag_factor_reg(const Dims& d, cplx* A, int
     __syncwarp();
 }
 
-#ifdef SBCE_CHOL_LOADS_FIRST
-// volatile: keeps its place among the (volatile) MMAs, i.e. at the top of the step
-__device__ __forceinline__ cplx ldg_v(const cplx* p) {
-    cplx v;
-    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-#endif
 __device__ __forceinline__ void spin_until_ge(const volatile int* p, int v) {
     while (*p < v) __nanosleep(20);
     __threadfence_block();
