@@ -195,9 +195,12 @@ def run_reference(args):
     w = workloads.WORKLOADS[args.config]
     wd = workload_dict(w)
     vals, last = [], None
+    # every step is one bounded sample: all host cores, one trial each, `it` EM iterations from the LS start,
+    # scaled to the full iteration count.  Long runs (the driver's --steps 20 --warmup 5) use one iteration per
+    # sample so that the whole run stays within a few minutes (~7 s per sample at the headline size).
+    it_timed = args.cpu_sample_iters if (args.steps + args.warmup) <= 12 else 1
     for i in range(args.warmup + args.steps):
-        # warm-up steps (untimed) run one EM iteration per worker, timed steps the bounded sample
-        r = cpu_sample(wd, args.cpu_sample_iters if i >= args.warmup else 1, seed=1000 + 97 * i)
+        r = cpu_sample(wd, it_timed if i >= args.warmup else 1, seed=1000 + 97 * i)
         if i >= args.warmup:
             vals.append(r)
         last = r

@@ -18,11 +18,20 @@ import numpy as np
 
 
 def _worker(args):
-    (seed, w, iters) = args
     try:
         from threadpoolctl import threadpool_limits
     except Exception:  # pragma: no cover
         threadpool_limits = None
+    # one BLAS thread per worker for the WHOLE worker: input generation (pinv, W @ Theta) with the default thread
+    # count oversubscribes the cores 16-fold and took 45 s of wall time per sample before the clock even started
+    if threadpool_limits is not None:
+        with threadpool_limits(limits=1):
+            return _worker_body(args)
+    return _worker_body(args)
+
+
+def _worker_body(args):
+    (seed, w, iters) = args
     from oracle import em_numpy as orc
 
     N, n_tx, n_rx, M, T_p, T_d, varn = w["N"], w["n_tx"], w["n_rx"], w["M"], w["T_p"], w["T_d"], w["varn"]
@@ -43,22 +52,16 @@ def _worker(args):
     Yd = orc.design_rows(PsiD, Xd) @ Th + nz(T_d)
     theta0 = None if w.get("zero_start") else np.linalg.pinv(Wp) @ Yp      # h_initial, PM.py:147
 
-    def run():
-        t0 = time.perf_counter()
-        if mode in ("soft", "hard"):
-            orc.em(Yd, Yp, PsiD, PsiP, Xp, M, varn, iters, theta0=theta0, hard=(mode == "hard"))
-        elif mode in ("pm", "pm_beta"):
-            orc.em_pm(Yd, Yp, PsiD, PsiP, Xp, M, varn, iters, theta0, h_true=Th, partition_r=w.get("partition_r", 0),
-                      weighted=(mode == "pm_beta"), genie_stop=False, quirks=w.get("quirks", True), how="solve")
-        else:
-            orc.em_detector(Yd, Yp, PsiD, PsiP, Xp, M, varn, iters, theta0, kind=mode, h_true=Th, genie_stop=False,
-                            quirks=w.get("quirks", True))
-        return time.perf_counter() - t0
-
-    if threadpool_limits is not None:
-        with threadpool_limits(limits=1):
-            return run()
-    return run()
+    t0 = time.perf_counter()
+    if mode in ("soft", "hard"):
+        orc.em(Yd, Yp, PsiD, PsiP, Xp, M, varn, iters, theta0=theta0, hard=(mode == "hard"))
+    elif mode in ("pm", "pm_beta"):
+        orc.em_pm(Yd, Yp, PsiD, PsiP, Xp, M, varn, iters, theta0, h_true=Th, partition_r=w.get("partition_r", 0),
+                  weighted=(mode == "pm_beta"), genie_stop=False, quirks=w.get("quirks", True), how="solve")
+    else:
+        orc.em_detector(Yd, Yp, PsiD, PsiP, Xp, M, varn, iters, theta0, kind=mode, h_true=Th, genie_stop=False,
+                        quirks=w.get("quirks", True))
+    return time.perf_counter() - t0
 
 
 def time_sample(w, sample_iters=2, workers=None, seed=1234):
