@@ -72,7 +72,7 @@ static int make_dims(const sbce_cfg* c, Dims* d, bool with_estep = true) {
     d->bitsM = (sq == 2 ? 2 : (sq == 4 ? 4 : 6));
     d->T_p = c->T_p; d->T_d = c->T_d; d->itera = c->itera;
     d->L = d->N1 * c->n_tx;
-    d->Lp = (d->L + 3) & ~3;
+    d->Lp = (d->L + 7) & ~7;   // rows of the factor start on 128-byte lines (chol.cu loads 8-column steps as one line)
     d->RP = (c->n_rx + 3) & ~3;
     d->Ltot = d->Lp + d->RP;
     d->mode = c->mode; d->flags = c->flags; d->p1 = c->partition_p1;

@@ -41,6 +41,18 @@
 //   L2 prefetch of the next block's rows in the back substitution                                      +-0
 //   back substitution as a separate warp-per-trial kernel                                          1.96 ms
 //   next step's fragment loads pinned to the top of the step (volatile asm; ptxas sinks them)   1.86 ms (+-0)
+//   CTA shapes at 128 registers (gpurun_out/r02p): 8 warps x 2 CTAs/SM 2.34 ms, 16 warps x 1 CTA/SM 3.80 ms,
+//     2 warps x 8 CTAs/SM 1.87 ms -- the factors of 2 resp. 1 resident trial per SM fit in L2, those of 4 do
+//     not: the trials in flight per SM matter, L2 residency does not
+//   96 registers / 5 CTAs per SM (680 bytes of spills), with or without the Gauss product             2.43 ms
+//   back substitution: W row as independent loads before the barrier + L1 prefetch of the next block   1.82 ms
+//     (both column rounds of the update fetched up front: spills, 2.02 ms)
+//   fragments as 256-bit loads on a permuted contraction index (halves the L1 wavefronts of a load)    1.81 ms
+//   L1 prefetch distance 0 / 1 / 2 / 3 steps                                        2.02 / 1.87 / 1.81 / 1.83 ms
+//   L1 prefetch of the 16 x 16 block to be updated four steps before the loop ends (its read-modify-write wait
+//     held 12.6 % of the warp samples, profiles/r02m) and of the block-row operand by the idle lanes   +-0.5 %
+//     -- removing single stall sites no longer moves the kernel: DRAM 40 %, L2->L1 5 TB/s, DMMA pipe 44 %, L1
+//     wavefronts 47 % are all half used; what is left is the number of independent trials per SM (registers)
 #include <math.h>
 
 #include "common.cuh"
@@ -262,20 +274,22 @@ __global__ void __launch_bounds__(CF_WARPS * 32, MINB) k_chol_solve(Dims d, cplx
             for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { cr[j][e] = 0.0; ci[j][e] = 0.0; if (GAUSS) p3[GAUSS ? j : 0][e] = 0.0; }
-            const cplx* pa0 = A + (size_t)ra * ld + tig;
-            const cplx* pa1 = A + (size_t)rb8 * ld + tig;
+            // the contraction index of a step is permuted: lane tig takes columns (2 tig, 2 tig + 1) of the step's 8
+            // as its k = tig and k = tig + 4 elements -- for BOTH operands, so the product is unchanged -- and fetches
+            // them as one 256-bit load (rows start on 128-byte lines: a fragment load touches 8 lines instead of 16)
+            const cplx* pa0 = A + (size_t)ra * ld + 2 * tig;
+            const cplx* pa1 = A + (size_t)rb8 * ld + 2 * tig;
             const cplx* pb[2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) pb[j] = A + (size_t)min(g0 + 8 * j + g, Ltot - 1) * ld + tig;
+            for (int j = 0; j < 2; ++j) pb[j] = A + (size_t)min(g0 + 8 * j + g, Ltot - 1) * ld + 2 * tig;
             // fragments are double-buffered in registers: the loads of step q+1 are in flight during the DMMAs of
             // step q (the tile rows stream from L2 / DRAM, the block rows hit L1)
             constexpr int NJ = 2;
             cplx fa[4], fb[NJ][2];
-            fa[0] = pa0[0]; fa[1] = pa1[0];
-            fa[2] = pa0[4]; fa[3] = pa1[4];
+            ldg256(pa0, fa[0], fa[2]);
+            ldg256(pa1, fa[1], fa[3]);
 #pragma unroll
-            for (int j = 0; j < NJ; ++j)
-                { fb[j][0] = pb[j][0]; fb[j][1] = pb[j][4]; }
+            for (int j = 0; j < NJ; ++j) ldg256(pb[j], fb[j][0], fb[j][1]);
             auto pair = [&](int j, const double (&ar)[4], const double (&ai)[4], const double (&as)[4], const cplx& b0,
                             const cplx& b1) {
                 if (GAUSS) {
@@ -289,19 +303,19 @@ __global__ void __launch_bounds__(CF_WARPS * 32, MINB) k_chol_solve(Dims d, cplx
                     dmma16x8x8(ci[j], ar, -b0.y, -b1.y);
                 }
             };
-            // L1 prefetch of the streamed operand PF steps ahead (no registers held): lanes 0-15 touch the line
-            // that holds the first, lanes 16-31 the line that holds the last element of their row's 128-byte segment
-            const cplx* ppf = A + (size_t)min(r0 + (lane & 15), Ltot - 1) * ld + ((lane >> 4) ? 7 : 0);
+            // L1 prefetch of the streamed operand PF steps ahead (no registers held): lane r < 16 touches the line
+            // that is row r's 8-column step
+            const cplx* ppf = A + (size_t)min(r0 + (lane & 15), Ltot - 1) * ld;
 #pragma unroll 1
             for (int q0 = 0; q0 < g0; q0 += 8) {
                 cplx na[4], nbf[NJ][2];
                 const int qn = (q0 + 8 < g0) ? q0 + 8 : q0;   // last step reloads itself (harmless, L1 hit)
-                if (PF > 0 && q0 + 8 * PF < g0) asm volatile("prefetch.global.L1 [%0];" ::"l"(ppf + q0 + 8 * PF));
-                na[0] = pa0[qn]; na[1] = pa1[qn];
-                na[2] = pa0[qn + 4]; na[3] = pa1[qn + 4];
+                if (PF > 0 && lane < 16 && q0 + 8 * PF < g0)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(ppf + q0 + 8 * PF));
+                ldg256(pa0 + qn, na[0], na[2]);
+                ldg256(pa1 + qn, na[1], na[3]);
 #pragma unroll
-                for (int j = 0; j < NJ; ++j)
-                    { nbf[j][0] = pb[j][qn]; nbf[j][1] = pb[j][qn + 4]; }
+                for (int j = 0; j < NJ; ++j) ldg256(pb[j] + qn, nbf[j][0], nbf[j][1]);
                 const double ar[4] = {fa[0].x, fa[1].x, fa[2].x, fa[3].x};
                 const double ai[4] = {fa[0].y, fa[1].y, fa[2].y, fa[3].y};
                 const double as[4] = {fa[0].x + fa[0].y, fa[1].x + fa[1].y, fa[2].x + fa[2].y, fa[3].x + fa[3].y};
@@ -366,19 +380,35 @@ __global__ void __launch_bounds__(CF_WARPS * 32, MINB) k_chol_solve(Dims d, cplx
         const int l = e / nrx, r = e % nrx;
         th[e] = cconj(A[(size_t)(Lp + r) * ld + l]);
     }
-    for (int k0 = ((Lp - 1) / CH_NB) * CH_NB; k0 >= 0; k0 -= CH_NB) {
+    // A thread's W row is fetched as 15 independent predicated loads BEFORE the barrier that precedes the dependent
+    // accumulation (the compiler's own unrolling left up to four serial L2 round trips per block), and the next
+    // diagonal block's 2 x 16 lines are pulled into L1 during the update phase of the current block.
+    const int kfirst = ((Lp - 1) / CH_NB) * CH_NB;
+    auto prefetch_w = [&](int k0) {
+        if (tid < 2 * CH_NB && k0 + (tid >> 1) < Lp)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(A + (size_t)(k0 + (tid >> 1)) * ld + k0 + 8 * (tid & 1)));
+    };
+    prefetch_w(kfirst);
+    for (int k0 = kfirst; k0 >= 0; k0 -= CH_NB) {
         const int nb = min(CH_NB, Lp - k0);
-        __syncthreads();  // th updates of the previous block are complete
         const bool act = tid < nb * nrx;
         const int bc = act ? tid / nrx : 0, br = act ? tid % nrx : 0;
+        cplx wv[CH_NB];
+        const cplx* wrow = A + (size_t)(k0 + bc) * ld + k0;
+        const double wd = wrow[bc].x;
+#pragma unroll
+        for (int q = 1; q < CH_NB; ++q) wv[q] = (act && q > bc && q < nb) ? wrow[q] : mk(0.0, 0.0);
+        __syncthreads();  // th updates of the previous block are complete
         cplx xv = mk(0.0, 0.0);
         if (act) {
-            const cplx* wrow = A + (size_t)(k0 + bc) * ld + k0;
-            xv = cscale(th[(k0 + bc) * nrx + br], 1.0 / wrow[bc].x);
-            for (int q = bc + 1; q < nb; ++q) cfmac(xv, th[(k0 + q) * nrx + br], wrow[q]);
+            xv = cscale(th[(k0 + bc) * nrx + br], 1.0 / wd);
+#pragma unroll
+            for (int q = 1; q < CH_NB; ++q)
+                if (q > bc && q < nb) cfmac(xv, th[(k0 + q) * nrx + br], wv[q]);
         }
         __syncthreads();
         if (act) th[(k0 + bc) * nrx + br] = xv;
+        if (k0 >= CH_NB) prefetch_w(k0 - CH_NB);
         __syncthreads();
         for (int c = tid; c < k0; c += CH_THREADS) {
             cplx cq[CH_NB];

@@ -56,4 +56,11 @@ __device__ __forceinline__ void cp_async16_ca(void* smem_dst, const void* gsrc) 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc));
 }
 
+// 256-bit global load (SASS LDG.E.256, sm_100+): two consecutive complex doubles of one row.  A warp-wide load is
+// served by the L1 one 128-byte line at a time, so fetching a lane's two k-elements as ONE 32-byte access instead
+// of two 16-byte accesses to the same line halves the L1 wavefronts of a fragment load.  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const double2* p, double2& a, double2& b) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+
 }  // namespace sbce
