@@ -53,6 +53,10 @@
 //     held 12.6 % of the warp samples, profiles/r02m) and of the block-row operand by the idle lanes   +-0.5 %
 //     -- removing single stall sites no longer moves the kernel: DRAM 40 %, L2->L1 5 TB/s, DMMA pipe 44 %, L1
 //     wavefronts 47 % are all half used; what is left is the number of independent trials per SM (registers)
+//   no register double buffer (operands read from L1 behind the prefetch): 4 CTAs/SM 1.84 ms; 5 CTAs/SM at 96
+//     registers 2.39 ms, 6 at 80 registers 3.20 ms (the register-resident diagonal factor spills 0.8 - 1.6 KB)
+//   L1 policies on the fragment loads (ld.global.lu / evict_first for the streamed rows, evict_last for the
+//     block rows) and the solution vector moved to global memory (L1 156 -> 224 KB)                     +-0.3 %
 #include <math.h>
 
 #include "common.cuh"
