@@ -168,6 +168,38 @@ def test_host_route_two_half_split_small_problem(S, orc):
         assert relerr(res.theta[b], ref) < RTOL and np.array_equal(res.kstar[b], tr["kstar"])
 
 
+def test_host_route_graph_replay_tracks_new_inputs(S):
+    """sbce_em_batch_host replays the kernel schedule of a call from a CUDA graph from the third call with the
+    same configuration on (abi.cu: run_half).  The replay must read the CURRENT call's inputs (same pool
+    addresses, new data), a changed configuration must not hit a stale graph, and the launch counter must
+    report a replayed call like an eager one."""
+    engine = S.engine
+    N, n_tx, n_rx, M, T_p, T_d, varn, B = 6, 2, 2, 4, 16, 24, 0.3, 48
+    sets = [S.signal_model.generate_batch(N, n_tx, n_rx, M, T_p, T_d, varn * (1 + i), B, seed=40 + i, legacy=False,
+                                          variant="top_tp") for i in range(2)]
+    expect = {}
+    for itera in (2, 3):
+        prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera)
+        for i, tb in enumerate(sets):
+            hin = dict(Yd=tb.Yd, Yp=tb.Yp, PsiD=tb.PsiD, PsiP=tb.PsiP, Xp=tb.Xp, theta0=tb.theta0, h_true=tb.h,
+                       varn=tb.varn)
+            expect[(itera, i)] = _run_device(S, prob, hin, B)
+    counts = []
+    # eager, capture, then replays -- alternating data sets, then a different iteration count, then back
+    order = [(2, 0), (2, 1), (2, 0), (2, 1), (2, 0), (3, 1), (3, 0), (3, 1), (2, 1), (3, 0)]
+    for itera, i in order:
+        tb = sets[i]
+        prob = S.Problem(N=N, n_tx=n_tx, n_rx=n_rx, M=M, T_p=T_p, T_d=T_d, itera=itera)
+        engine.launch_count(reset=True)
+        res = S.run_host(prob, tb.Yd, tb.Yp, tb.PsiD, tb.PsiP, tb.Xp, tb.varn, theta0=tb.theta0, h_true=tb.h)
+        counts.append((itera, engine.launch_count()))
+        for k in ("theta", "kstar", "lse", "nmse", "iters", "status"):
+            assert same(getattr(res, k), expect[(itera, i)][k]), (itera, i, k)
+    for itera in (2, 3):
+        c = {n for it, n in counts if it == itera}
+        assert len(c) == 1 and min(c) > 0, counts
+
+
 def test_partitioned_modes_report_no_decisions(S):
     """PM / PM-beta take no joint decision and form no log-sum: kstar must read -1 and lse NaN on every call
     (not whatever the buffers held), and the sweep drivers must not turn them into a symbol error rate."""
