@@ -535,7 +535,15 @@ __device__ __noinline__ void enum_flush(double* ws, double warp_best) {
             const double E0 = W * EI * EQ;
             const cplx F0 = mk(W * A1 * EQ, -W * EI * B1);  // sum over leaves of e * conj(x_0)
             const double Q0 = W * (A2 * EQ + EI * B2);      // sum over leaves of e * |x_0|^2
-            auto add = [&](int idx, double v) { if ((idx & 31) == lane) A[idx] += v; };
+            // statistic idx belongs to lane idx & 31: every lane picks its values out of the (warp-uniform) results
+            // with predicated register moves and then makes ONE shared-memory update per 32 statistics (as ~25
+            // single-lane read-modify-writes behind divergent branches this was 14 % of the kernel's stall
+            // samples, profiles/r02m); per entry, so the order of the additions is unchanged
+            constexpr int NR = (E::NACC + 31) / 32;
+            double mine[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) mine[r] = 0.0;
+            auto add = [&](int idx, double v) { if ((idx & 31) == lane) mine[idx >> 5] = v; };
             add(0, E0);
             add(1, F0.x);
             add(1 + NTX, F0.y);
@@ -558,6 +566,9 @@ __device__ __noinline__ void enum_flush(double* ws, double warp_best) {
                         add(1 + 3 * NTX + 2 * E::pair(i, s) + 1, E0 * cx.y);
                     }
             }
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+                if (32 * r + lane < E::NACC) A[32 * r + lane] += mine[r];
             __syncwarp();
         }
         if (lane == 0) {
