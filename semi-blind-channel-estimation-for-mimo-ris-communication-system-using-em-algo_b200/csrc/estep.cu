@@ -805,10 +805,17 @@ __global__ void __launch_bounds__(WARPS * 32, (NTX > 4 ? 2 : 4)) k_enum(Dims d, 
     constexpr int M = E::M;
     extern __shared__ __align__(16) double enum_smem[];   // [WARPS][E::WS_DOUBLES]
     const int b = blockIdx.y;
-    if (active != nullptr && active[b] == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * WARPS + warp;
     if (t >= d.T_d) return;
+    // the three global reads a warp starts with -- trial flag, noise variance, first 32 doubles of the QR record --
+    // are issued together (one after the other they were three DRAM round trips before the first useful
+    // instruction, 10 % of the kernel's stall samples in profiles/r02m)
+    const double* grec = qr + ((size_t)b * d.T_d + t) * d.rec;
+    const int32_t act = (active != nullptr) ? active[b] : 1;
+    const double vn = varn[b];
+    const double rec0 = (lane < d.rec) ? grec[lane] : 0.0;
+    if (act == 0) return;
 
     double* ws = enum_smem + (size_t)warp * E::WS_DOUBLES;
     cplx* tab = (cplx*)(ws + E::O_TAB);
@@ -817,8 +824,8 @@ __global__ void __launch_bounds__(WARPS * 32, (NTX > 4 ? 2 : 4)) k_enum(Dims d, 
     // broadcast reads from shared memory (every lane needs all of it; 30+ uniform global loads per lane before)
     const double* rec = ws + E::O_SCR;
     {
-        const double* grec = qr + ((size_t)b * d.T_d + t) * d.rec;
-        for (int i = lane; i < d.rec; i += 32) ws[E::O_SCR + i] = grec[i];
+        if (lane < d.rec) ws[E::O_SCR + lane] = rec0;
+        for (int i = lane + 32; i < d.rec; i += 32) ws[E::O_SCR + i] = grec[i];
         __syncwarp();
     }
     cplx yt[NTX];
@@ -857,7 +864,6 @@ __global__ void __launch_bounds__(WARPS * 32, (NTX > 4 ? 2 : 4)) k_enum(Dims d, 
         }
     }
     const double c0 = rec[NTX * (NTX + 1) + 2 * NTX];
-    const double vn = varn[b];
     const double s2 = vn * vn, inv_s2 = 1.0 / s2;
     if (lane == 0) {
 #pragma unroll
@@ -969,23 +975,26 @@ __global__ void __launch_bounds__(WARPS * 32, (NTX > 4 ? 2 : 4)) k_enum(Dims d, 
         }
         return;
     }
-    if (lane == 0) {
+    // outputs: lane l < n_tx^2 writes R[i][j] with (i, j) = (l / n_tx, l % n_tx), lane j < n_tx writes m[j] -- two
+    // coalesced stores (lane 0 alone issued all n_tx + n_tx^2 of them one after the other before)
+    {
         const double invS = 1.0 / S;
         const double* A = ws + E::O_ACC;
-#pragma unroll
-        for (int j = 0; j < NTX; ++j) {
-            stat_m[sidx * NTX + j] = mk(A[1 + j] * invS, A[1 + NTX + j] * invS);
-            stat_R[(sidx * NTX + j) * NTX + j] = mk(A[1 + 2 * NTX + j] * invS, 0.0);
-        }
-#pragma unroll
-        for (int s = 1; s < NTX; ++s)
-#pragma unroll
-            for (int i = 0; i < s; ++i) {
-                const double a = A[1 + 3 * NTX + 2 * E::pair(i, s)] * invS, c = A[1 + 3 * NTX + 2 * E::pair(i, s) + 1] * invS;
-                stat_R[(sidx * NTX + i) * NTX + s] = mk(a, c);
-                stat_R[(sidx * NTX + s) * NTX + i] = mk(a, -c);
+        for (int l = lane; l < NTX * NTX; l += 32) {
+            const int i = l / NTX, j = l % NTX;
+            cplx v;
+            if (i == j) {
+                v = mk(A[1 + 2 * NTX + j] * invS, 0.0);
+            } else {
+                const int lo = min(i, j), hi = max(i, j);
+                const int pr = 1 + 3 * NTX + 2 * E::pair(lo, hi);
+                const double a = A[pr] * invS, c = A[pr + 1] * invS;
+                v = mk(a, i < j ? c : -c);
             }
-        if (lse_sym != nullptr) lse_sym[sidx] = -ws[E::O_AREF] * inv_s2 + log(S);
+            stat_R[sidx * NTX * NTX + l] = v;
+        }
+        if (lane < NTX) stat_m[sidx * NTX + lane] = mk(A[1 + lane] * invS, A[1 + NTX + lane] * invS);
+        if (lse_sym != nullptr && lane == 0) lse_sym[sidx] = -ws[E::O_AREF] * inv_s2 + log(S);
     }
 }
 
