@@ -23,7 +23,7 @@ for f in sorted(os.listdir(G)):
 launch = os.path.join(G, tag + "_launches.csv")
 if os.path.exists(launch):
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), "launches", launch,
-                    os.path.join(P, tag + "_launches.md"), "python bench.py --steps 2 --warmup 3 --kernels-only"],
+                    os.path.join(P, tag + "_launches.md"), "python bench.py --steps 1 --warmup 3 --kernels-only"],
                    stdout=subprocess.DEVNULL)
     print("wrote", tag + "_launches.md")
 rep = os.path.join(G, tag + "_full.ncu-rep")
