@@ -494,6 +494,12 @@ int pool_get(int dev, size_t bytes, DevPool** out) {
         CK(cudaEventCreateWithFlags(&P.ev[1], cudaEventDisableTiming));
     }
     if (P.cap < bytes) {
+        // the cached graphs hold addresses inside the old allocation (both streams are idle here: every call
+        // drains them before it returns)
+        for (GraphSlot& g : P.graphs) {
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+            g = GraphSlot();
+        }
         if (P.p) CK(cudaFree(P.p));
         P.p = nullptr;
         P.cap = 0;
