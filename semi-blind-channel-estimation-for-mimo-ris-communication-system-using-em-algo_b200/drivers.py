@@ -14,8 +14,8 @@ per-point accumulators are summed once at the end (dist.allreduce_sum).
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field, replace
-from typing import Callable, List, Optional, Sequence
+from dataclasses import dataclass, replace
+from typing import Callable, List, Sequence
 
 import numpy as np
 

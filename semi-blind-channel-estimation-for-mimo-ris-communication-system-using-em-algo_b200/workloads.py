@@ -9,7 +9,7 @@ oracle/make_config_golden.py with the same `make_batch` inputs).
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 

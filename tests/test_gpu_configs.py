@@ -12,7 +12,6 @@ The oracle needs minutes per trial at these sizes, so its outputs are committed 
 (tests/golden/config_*.npz, minted by oracle/make_config_golden.py); every test first proves (SHA-256 of the
 integer draws, projections of the floating arrays) that it regenerated the inputs the fixture was minted from.
 """
-import dataclasses
 
 import numpy as np
 import pytest
