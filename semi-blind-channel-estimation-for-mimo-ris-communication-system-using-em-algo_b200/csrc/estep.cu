@@ -733,16 +733,18 @@ struct Scan {
             if (__all_sync(0xffffffffu, dead)) return;
             // innermost node level: |u_1|^2 and R_01 x_1 are separable in the in-phase / quadrature indices
             const double* g1 = g + SQM;
-            double dI1[SQM], dQ1[SQM];
+            double dI1[SQM];
 #pragma unroll
             for (int a = 0; a < SQM; ++a) {
-                const double eI = acc[1].x - g1[a], eQ = acc[1].y - g1[a];
+                const double eI = acc[1].x - g1[a];
                 dI1[a] = eI * eI;
-                dQ1[a] = eQ * eQ;
             }
 #pragma unroll 1
             for (int iQ = 0; iQ < SQM; ++iQ) {
-                const double bq = base + dQ1[iQ];
+                // the quadrature term is formed here (a table indexed by the loop counter lived in local memory);
+                // product and sum are rounded separately, as the table version did
+                const double eQ = acc[1].y - g1[iQ];
+                const double bq = base + __dmul_rn(eQ, eQ);
                 const bool deadq = dead || (prune && bq > lim);
                 if (__all_sync(0xffffffffu, deadq)) continue;
                 const double pQ = E::pam(iQ);
