@@ -117,3 +117,13 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
     assert line["config"]["N"] == 32 and line["gpu_launches"] == 0
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    """Launched under torchrun with N > 1 the reference arm runs on rank 0 only: every other rank exits 0 without
+    work and without printing a line."""
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip() == ""
